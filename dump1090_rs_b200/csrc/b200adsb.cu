@@ -1,0 +1,1088 @@
+// dump1090_rs_b200/csrc/b200adsb.cu -- C ABI (include/b200adsb.h) over the kernels.
+//
+// Host side of libb200adsb.so: context (device buffers, stream, ICAO filter state
+// resident on the GPU), the staged pipeline scan -> [event exchange] -> finalise ->
+// resolve -> ordered emit -> commit, and the host<->device plumbing.  No torch, no
+// CPU compute path: if CUDA is unavailable every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace b200;
+
+namespace {
+
+constexpr uint32_t kEvSlots = 1u << 16;
+constexpr size_t kMaxStageBytes = 2ull << 30;   // host batch API: IQ staged per pass
+
+struct EventPair {
+    cudaEvent_t a, b;
+};
+
+struct Pending {
+    bool active = false;
+    const void *in = nullptr;
+    bool from_mag = false;
+    const uint32_t *lengths = nullptr;
+    uint32_t n_buffers = 0, spb = 0, n_tiles = 0;
+    unsigned long long stride = 0;
+    int T = 0, tpb = 0;
+    unsigned long long ord_first = 0, ord_stride = 1;
+    const uint8_t *msgs = nullptr;   // message-level API
+};
+
+}  // namespace
+
+struct b200adsb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = false;
+    int tile_opt = 0, pool_shift = 5, profile = 0, h2d_chunk = 64;
+
+    uint32_t *d_counters = nullptr, *h_counters = nullptr;
+    uint32_t *d_members = nullptr;
+    uint32_t *d_ev_keys = nullptr, *d_ev_used = nullptr, *d_ev_tmp = nullptr, *d_new_keys = nullptr;
+    unsigned long long *d_ev_ord = nullptr;
+    uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr;
+    uint32_t *d_scalar = nullptr;
+
+    uint32_t *d_rec = nullptr, *d_emit_info = nullptr;
+    int32_t *d_rec_score = nullptr;
+    size_t pool_cap = 0;
+    uint2 *d_tile_dir = nullptr;
+    uint32_t *d_tile_emit = nullptr;
+    size_t tiles_cap = 0;
+
+    void *d_stage = nullptr;
+    size_t stage_bytes = 0;
+    b200adsb_frame *d_frames = nullptr;
+    size_t frames_cap = 0;
+    uint32_t *d_counts = nullptr;
+    size_t counts_cap = 0;
+    uint32_t *d_lengths = nullptr;
+    size_t lengths_cap = 0;
+
+    unsigned long long next_ordinal = 0;   // stream position (buffers) for the fused entry points
+    Pending cur;
+    std::vector<EventPair> scan_events, other_events;
+    std::vector<cudaEvent_t> chunk_events;
+    b200adsb_timing timing{};
+    char err[256] = {0};
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                     \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                     cudaGetErrorString(e_));                                             \
+            return B200ADSB_ERR_CUDA;                                                     \
+        }                                                                                 \
+    } while (0)
+
+uint32_t crc_pow(int e)   // x^e mod G, G = x^24 + 0xFFF409
+{
+    uint32_t s = 1;
+    for (int i = 0; i < e; i++) {
+        s <<= 1;
+        if (s & 0x1000000u)
+            s ^= 0x1FFF409u;
+    }
+    return s;
+}
+
+// Field tables of kernels.cuh::a112/a56: field bit m of field r is message bit 5m+r.
+//   a112(f) = sum_{m<=21} f[m] x^(107-5m),  a56(f) = sum_{m<=10} f[m] x^(51-5m)
+void build_crc_tabs(uint32_t *t, uint32_t *t256)
+{
+    auto fill = [&](uint32_t *dst, int entries, int m0, int e_base) {
+        for (int v = 0; v < entries; v++) {
+            uint32_t s = 0;
+            for (int bit = 0; (1 << bit) < entries; bit++)
+                if (v & (1 << bit))
+                    s ^= crc_pow(e_base - 5 * (m0 + bit));
+            dst[v] = s;
+        }
+    };
+    fill(t, 256, 0, 107);
+    fill(t + 256, 256, 8, 107);
+    fill(t + 512, 64, 16, 107);
+    fill(t + kTab56, 256, 0, 51);
+    fill(t + kTab56 + 256, 8, 8, 51);
+    for (uint32_t i = 0; i < 256; i++) {   // src/crc.rs:3-260, generated from the polynomial
+        uint32_t c = i << 16;
+        for (int k = 0; k < 8; k++)
+            c = (c & 0x800000u) ? ((c << 1) ^ 0xFFF409u) : (c << 1);
+        t256[i] = c & 0xFFFFFFu;
+    }
+}
+
+int bind(b200adsb_ctx *c)
+{
+    CK(c, cudaSetDevice(c->device));
+    return B200ADSB_OK;
+}
+
+template <typename T>
+int grow(b200adsb_ctx *c, T **p, size_t *cap, size_t need, size_t elem = sizeof(T))
+{
+    if (need <= *cap && *p)
+        return B200ADSB_OK;
+    if (*p)
+        CK(c, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    const size_t n = std::max<size_t>(need, 1);
+    cudaError_t e = cudaMalloc((void **)p, n * elem);
+    if (e != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "cudaMalloc(%zu bytes): %s", n * elem, cudaGetErrorString(e));
+        return B200ADSB_ERR_NOMEM;
+    }
+    *cap = n;
+    return B200ADSB_OK;
+}
+
+int ensure_pool(b200adsb_ctx *c, size_t need)
+{
+    if (need <= c->pool_cap && c->d_rec)
+        return B200ADSB_OK;
+    if (c->d_rec) CK(c, cudaFree(c->d_rec));
+    if (c->d_emit_info) CK(c, cudaFree(c->d_emit_info));
+    if (c->d_rec_score) CK(c, cudaFree(c->d_rec_score));
+    c->d_rec = c->d_emit_info = nullptr;
+    c->d_rec_score = nullptr;
+    c->pool_cap = 0;
+    cudaError_t e = cudaMalloc((void **)&c->d_rec, need * 24);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_emit_info, need * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_rec_score, need * 4);
+    if (e != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "candidate pool (%zu records): %s", need, cudaGetErrorString(e));
+        return B200ADSB_ERR_NOMEM;
+    }
+    c->pool_cap = need;
+    return B200ADSB_OK;
+}
+
+int ensure_tiles(b200adsb_ctx *c, size_t n_tiles)
+{
+    if (n_tiles <= c->tiles_cap && c->d_tile_dir)
+        return B200ADSB_OK;
+    if (c->d_tile_dir) CK(c, cudaFree(c->d_tile_dir));
+    if (c->d_tile_emit) CK(c, cudaFree(c->d_tile_emit));
+    c->d_tile_dir = nullptr;
+    c->d_tile_emit = nullptr;
+    c->tiles_cap = 0;
+    cudaError_t e = cudaMalloc((void **)&c->d_tile_dir, n_tiles * sizeof(uint2));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_tile_emit, (n_tiles + 1) * 4);
+    if (e != cudaSuccess) {
+        snprintf(c->err, sizeof(c->err), "tile directory (%zu): %s", n_tiles, cudaGetErrorString(e));
+        return B200ADSB_ERR_NOMEM;
+    }
+    c->tiles_cap = n_tiles;
+    return B200ADSB_OK;
+}
+
+int pick_tile(const b200adsb_ctx *c, size_t n_buffers, size_t spb)
+{
+    if (c->tile_opt)
+        return c->tile_opt;
+    const size_t total = n_buffers * spb;
+    size_t t = total / 592;          // aim at >= 4 tiles per SM
+    t = t / 32 * 32;
+    return (int)std::min<size_t>(std::max<size_t>(t, 512), kMaxTile);
+}
+
+void prof_begin(b200adsb_ctx *c, std::vector<EventPair> &v)
+{
+    if (!c->profile)
+        return;
+    EventPair p;
+    cudaEventCreate(&p.a);
+    cudaEventCreate(&p.b);
+    cudaEventRecord(p.a, c->stream);
+    v.push_back(p);
+}
+void prof_end(b200adsb_ctx *c, std::vector<EventPair> &v)
+{
+    if (!c->profile)
+        return;
+    cudaEventRecord(v.back().b, c->stream);
+}
+void prof_collect(b200adsb_ctx *c)   // after a stream sync
+{
+    for (auto &p : c->scan_events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+            c->timing.scan_ms += ms;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    for (auto &p : c->other_events) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+            c->timing.resolve_ms += ms;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    c->scan_events.clear();
+    c->other_events.clear();
+}
+
+int read_counters(b200adsb_ctx *c)
+{
+    CK(c, cudaMemcpyAsync(c->h_counters, c->d_counters, C_WORDS * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return B200ADSB_OK;
+}
+
+// launch the scan kernel over buffers [b0, b0+nb) of the pending batch
+int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
+{
+    const Pending &q = c->cur;
+    ScanParams p{};
+    if (q.from_mag)
+        p.in = reinterpret_cast<const uint16_t *>(q.in) + (size_t)b0 * q.stride;
+    else
+        p.in = reinterpret_cast<const int16_t *>(q.in) + 2 * (size_t)b0 * q.stride;
+    p.lengths = q.lengths ? q.lengths + b0 : nullptr;
+    p.n_buffers = nb;
+    p.spb = q.spb;
+    p.stride = q.stride;
+    p.T = q.T;
+    p.tiles_per_buffer = q.tpb;
+    p.vec_ok = (!q.from_mag && ((uintptr_t)q.in % 16 == 0) && (q.stride % 4 == 0)) ? 1 : 0;
+    p.rec = c->d_rec;
+    p.pool_cap = (uint32_t)std::min<size_t>(c->pool_cap, 0xffffffffu);
+    p.tile_dir = c->d_tile_dir + (size_t)b0 * q.tpb;
+    p.counters = c->d_counters;
+    p.ev_keys = c->d_ev_keys;
+    p.ev_ord = c->d_ev_ord;
+    p.ev_used = c->d_ev_used;
+    p.ev_mask = kEvSlots - 1;
+    p.ord_first = q.ord_first + (unsigned long long)b0 * q.ord_stride;
+    p.ord_stride = q.ord_stride;
+    p.crc_tabs = c->d_crc_tabs;
+    const ScanSmem L(q.T);
+    const uint32_t grid = nb * (uint32_t)q.tpb;
+    if (grid == 0)
+        return B200ADSB_OK;
+    prof_begin(c, c->scan_events);
+    if (q.from_mag) {
+        CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+        scan_kernel<true><<<grid, kThreads, L.bytes, c->stream>>>(p);
+    } else {
+        CK(c, cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+        scan_kernel<false><<<grid, kThreads, L.bytes, c->stream>>>(p);
+    }
+    prof_end(c, c->scan_events);
+    CK(c, cudaGetLastError());
+    c->timing.scan_launches++;
+    c->timing.samples += (uint64_t)nb * q.spb;
+    return B200ADSB_OK;
+}
+
+int reset_scan_counters(b200adsb_ctx *c)
+{
+    // C_POOL, C_FLAGS cleared; C_CAND cleared; filter-full flag is per batch too
+    CK(c, cudaMemsetAsync(c->d_counters + C_POOL, 0, 8, c->stream));
+    CK(c, cudaMemsetAsync(c->d_counters + C_CAND, 0, 4, c->stream));
+    return B200ADSB_OK;
+}
+
+int clear_events(b200adsb_ctx *c)
+{
+    events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
+                                                    c->d_new_keys, c->d_counters, c->d_members);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+// set up a pending batch and run stage 1 (with pool growth); on return the scan is complete
+int scan_begin(b200adsb_ctx *c, const void *d_in, bool from_mag, size_t n_buffers, size_t spb,
+               size_t stride, const uint32_t *d_lengths, unsigned long long ord_first,
+               unsigned long long ord_stride)
+{
+    if (c->cur.active)
+        return B200ADSB_ERR_STATE;
+    if (spb > (size_t)kMaxSamples || n_buffers > 0xffffffu)
+        return B200ADSB_ERR_BAD_ARG;
+    Pending &q = c->cur;
+    q = Pending();
+    q.in = d_in;
+    q.from_mag = from_mag;
+    q.lengths = d_lengths;
+    q.n_buffers = (uint32_t)n_buffers;
+    q.spb = (uint32_t)spb;
+    q.stride = stride;
+    q.T = pick_tile(c, n_buffers, spb);
+    q.tpb = spb ? (int)((spb + q.T - 1) / q.T) : 0;
+    q.n_tiles = (uint32_t)(n_buffers * (size_t)q.tpb);
+    q.ord_first = ord_first;
+    q.ord_stride = ord_stride;
+    int rc = ensure_tiles(c, std::max<size_t>(q.n_tiles, 1));
+    if (rc) return rc;
+    const size_t positions = n_buffers * spb;
+    rc = ensure_pool(c, std::max<size_t>(positions >> c->pool_shift, 4096));
+    if (rc) return rc;
+    q.active = true;
+    return B200ADSB_OK;
+}
+
+// runs/re-runs stage 1 over the whole pending batch until the pool suffices
+int scan_run_all(b200adsb_ctx *c)
+{
+    Pending &q = c->cur;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        int rc = reset_scan_counters(c);
+        if (rc) return rc;
+        rc = launch_scan(c, 0, q.n_buffers);
+        if (rc) return rc;
+        rc = read_counters(c);
+        if (rc) return rc;
+        const uint32_t flags = c->h_counters[C_FLAGS];
+        if (flags & F_EV_OVF) {
+            clear_events(c);
+            q.active = false;
+            return B200ADSB_ERR_EVENTS;
+        }
+        if (!(flags & F_POOL_OVF))
+            return B200ADSB_OK;
+        // candidate pool too small: recycle the partial events, grow, redo
+        rc = clear_events(c);
+        if (rc) return rc;
+        const size_t need = (size_t)c->h_counters[C_POOL];
+        rc = ensure_pool(c, need + need / 8 + 1024);
+        if (rc) return rc;
+    }
+    q.active = false;
+    return B200ADSB_ERR_NOMEM;
+}
+
+int check_scan_flags(b200adsb_ctx *c, bool *redo)
+{
+    *redo = false;
+    int rc = read_counters(c);
+    if (rc) return rc;
+    const uint32_t flags = c->h_counters[C_FLAGS];
+    if (flags & F_EV_OVF) {
+        clear_events(c);
+        c->cur.active = false;
+        return B200ADSB_ERR_EVENTS;
+    }
+    if (flags & F_POOL_OVF) {
+        rc = clear_events(c);
+        if (rc) return rc;
+        const size_t need = (size_t)c->h_counters[C_POOL];
+        rc = ensure_pool(c, need + need / 8 + 1024);
+        if (rc) return rc;
+        *redo = true;
+    }
+    return B200ADSB_OK;
+}
+
+// stage 2: finalise events, resolve, ordered emit, commit
+int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
+                uint32_t *d_per_buffer_counts)
+{
+    Pending &q = c->cur;
+    if (!q.active)
+        return B200ADSB_ERR_STATE;
+    prof_begin(c, c->other_events);
+    events_finalize_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
+                                                      c->d_ev_tmp, c->d_new_keys, c->d_counters,
+                                                      c->d_members);
+    CK(c, cudaGetLastError());
+    if (q.n_tiles) {
+        ResolveParams rp{};
+        rp.rec = c->d_rec;
+        rp.tile_dir = c->d_tile_dir;
+        rp.n_tiles = q.n_tiles;
+        rp.tiles_per_buffer = q.tpb;
+        rp.emit_info = c->d_emit_info;
+        rp.tile_emit = c->d_tile_emit;
+        rp.rec_score = c->d_rec_score;
+        rp.members = c->d_members;
+        rp.ev_keys = c->d_ev_keys;
+        rp.ev_ord = c->d_ev_ord;
+        rp.ev_mask = kEvSlots - 1;
+        rp.ord_first = q.ord_first;
+        rp.ord_stride = q.ord_stride;
+        const uint32_t g = (q.n_tiles + kWarps - 1) / kWarps;
+        resolve_kernel<<<g, kThreads, 0, c->stream>>>(rp);
+        CK(c, cudaGetLastError());
+    }
+    tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_emit, q.n_tiles, c->d_counters);
+    CK(c, cudaGetLastError());
+    if (d_per_buffer_counts && q.n_buffers) {
+        buffer_counts_kernel<<<(q.n_buffers + 255) / 256, 256, 0, c->stream>>>(
+            c->d_tile_emit, q.n_buffers, q.tpb, q.n_tiles, c->d_counters, d_per_buffer_counts);
+        CK(c, cudaGetLastError());
+        c->timing.other_launches++;
+    }
+    if (q.n_tiles) {
+        EmitParams ep{};
+        ep.in = q.in;
+        ep.lengths = q.lengths;
+        ep.spb = q.spb;
+        ep.stride = q.stride;
+        ep.rec = c->d_rec;
+        ep.tile_dir = c->d_tile_dir;
+        ep.emit_info = c->d_emit_info;
+        ep.tile_excl = c->d_tile_emit;
+        ep.n_tiles = q.n_tiles;
+        ep.tiles_per_buffer = q.tpb;
+        ep.out = d_out;
+        ep.cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
+        ep.msgs = q.msgs;
+        const uint32_t g = (q.n_tiles + kWarps - 1) / kWarps;
+        if (q.from_mag)
+            emit_kernel<true><<<g, kThreads, 0, c->stream>>>(ep);
+        else
+            emit_kernel<false><<<g, kThreads, 0, c->stream>>>(ep);
+        CK(c, cudaGetLastError());
+    }
+    events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
+                                                    c->d_new_keys, c->d_counters, c->d_members);
+    CK(c, cudaGetLastError());
+    prof_end(c, c->other_events);
+    c->timing.other_launches += 5;
+    int rc = read_counters(c);
+    q.active = false;
+    if (rc) return rc;
+    c->timing.candidates += c->h_counters[C_CAND];
+    const size_t n = c->h_counters[C_FRAMES];
+    if (n_out)
+        *n_out = n;
+    return n > cap ? B200ADSB_ERR_CAPACITY : B200ADSB_OK;
+}
+
+int ensure_stage(b200adsb_ctx *c, size_t bytes)
+{
+    return grow(c, (unsigned char **)&c->d_stage, &c->stage_bytes, bytes, 1);
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int b200adsb_version(void) { return 100; }
+
+const char *b200adsb_strerror(int s)
+{
+    switch (s) {
+    case B200ADSB_OK: return "ok";
+    case B200ADSB_ERR_BAD_ARG: return "bad argument";
+    case B200ADSB_ERR_CAPACITY: return "output capacity exceeded";
+    case B200ADSB_ERR_CUDA: return "CUDA error";
+    case B200ADSB_ERR_NOMEM: return "out of device memory";
+    case B200ADSB_ERR_STATE: return "call out of order";
+    case B200ADSB_ERR_EVENTS: return "too many distinct new ICAO addresses in one batch";
+    default: return "unknown status";
+    }
+}
+
+const char *b200adsb_last_error(const b200adsb_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+
+int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
+{
+    if (!out)
+        return B200ADSB_ERR_BAD_ARG;
+    *out = nullptr;
+    b200adsb_ctx *c = new (std::nothrow) b200adsb_ctx();
+    if (!c)
+        return B200ADSB_ERR_NOMEM;
+    c->device = device;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        delete c;
+        return B200ADSB_ERR_CUDA;   // no CPU fallback: without a GPU there is no context
+    }
+    auto fail = [&](int rc) {
+        b200adsb_ctx_destroy(c);
+        return rc;
+    };
+#define CKC(call)                          \
+    do {                                   \
+        if ((call) != cudaSuccess)         \
+            return fail(B200ADSB_ERR_CUDA); \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc((void **)&c->d_counters, C_WORDS * 4));
+    CKC(cudaMemset(c->d_counters, 0, C_WORDS * 4));
+    CKC(cudaMallocHost((void **)&c->h_counters, C_WORDS * 4));
+    CKC(cudaMalloc((void **)&c->d_members, kMemberSlots * 4));
+    CKC(cudaMemset(c->d_members, 0, kMemberSlots * 4));
+    CKC(cudaMalloc((void **)&c->d_ev_keys, kEvSlots * 4));
+    CKC(cudaMemset(c->d_ev_keys, 0, kEvSlots * 4));
+    CKC(cudaMalloc((void **)&c->d_ev_ord, kEvSlots * 8));
+    CKC(cudaMemset(c->d_ev_ord, 0xff, kEvSlots * 8));
+    CKC(cudaMalloc((void **)&c->d_ev_used, kEvSlots * 4));
+    CKC(cudaMalloc((void **)&c->d_ev_tmp, kEvSlots * 4));
+    CKC(cudaMalloc((void **)&c->d_new_keys, (size_t)B200ADSB_ICAO_FILTER_SIZE * 4));
+    CKC(cudaMalloc((void **)&c->d_crc_tabs, kTabWords * 4));
+    CKC(cudaMalloc((void **)&c->d_crc256, 256 * 4));
+    CKC(cudaMalloc((void **)&c->d_scalar, 64));
+    {
+        uint32_t t[kTabWords], t256[256];
+        build_crc_tabs(t, t256);
+        CKC(cudaMemcpy(c->d_crc_tabs, t, sizeof t, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_crc256, t256, sizeof t256, cudaMemcpyHostToDevice));
+    }
+#undef CKC
+    *out = c;
+    return B200ADSB_OK;
+}
+
+void b200adsb_ctx_destroy(b200adsb_ctx *c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    prof_collect(c);
+    for (auto e : c->chunk_events)
+        cudaEventDestroy(e);
+    cudaFree(c->d_counters);
+    if (c->h_counters) cudaFreeHost(c->h_counters);
+    cudaFree(c->d_members);
+    cudaFree(c->d_ev_keys);
+    cudaFree(c->d_ev_ord);
+    cudaFree(c->d_ev_used);
+    cudaFree(c->d_ev_tmp);
+    cudaFree(c->d_new_keys);
+    cudaFree(c->d_crc_tabs);
+    cudaFree(c->d_crc256);
+    cudaFree(c->d_scalar);
+    cudaFree(c->d_rec);
+    cudaFree(c->d_emit_info);
+    cudaFree(c->d_rec_score);
+    cudaFree(c->d_tile_dir);
+    cudaFree(c->d_tile_emit);
+    cudaFree(c->d_stage);
+    cudaFree(c->d_frames);
+    cudaFree(c->d_counts);
+    cudaFree(c->d_lengths);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int b200adsb_ctx_set_option(b200adsb_ctx *c, int option, int64_t value)
+{
+    if (!c)
+        return B200ADSB_ERR_BAD_ARG;
+    switch (option) {
+    case B200ADSB_OPT_TILE:
+        if (value != 0 && (value < 32 || value > kMaxTile || value % 32))
+            return B200ADSB_ERR_BAD_ARG;
+        c->tile_opt = (int)value;
+        return B200ADSB_OK;
+    case B200ADSB_OPT_POOL_SHIFT:
+        if (value < 0 || value > 16)
+            return B200ADSB_ERR_BAD_ARG;
+        c->pool_shift = (int)value;
+        return B200ADSB_OK;
+    case B200ADSB_OPT_PROFILE:
+        c->profile = value ? 1 : 0;
+        return B200ADSB_OK;
+    case B200ADSB_OPT_H2D_CHUNK:
+        if (value < 1)
+            return B200ADSB_ERR_BAD_ARG;
+        c->h2d_chunk = (int)value;
+        return B200ADSB_OK;
+    default:
+        return B200ADSB_ERR_BAD_ARG;
+    }
+}
+
+int b200adsb_ctx_sync(b200adsb_ctx *c)
+{
+    if (!c)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    CK(c, cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    return B200ADSB_OK;
+}
+
+int b200adsb_timing_get(b200adsb_ctx *c, b200adsb_timing *out, int reset)
+{
+    if (!c || !out)
+        return B200ADSB_ERR_BAD_ARG;
+    *out = c->timing;
+    if (reset)
+        c->timing = b200adsb_timing{};
+    return B200ADSB_OK;
+}
+
+void *b200adsb_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess)
+        return nullptr;
+    return p;
+}
+void b200adsb_host_free(void *p)
+{
+    if (p)
+        cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ to_mag
+int b200adsb_to_mag(b200adsb_ctx *c, const int16_t *iq, size_t n, uint16_t *data, size_t *length)
+{
+    if (!c || (!iq && n) || !data)
+        return B200ADSB_ERR_BAD_ARG;
+    if (n > (size_t)kMaxSamples)
+        return B200ADSB_ERR_BAD_ARG;   // reference: index out of bounds panic, lib.rs:48
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = ensure_stage(c, (size_t)kMaxSamples * 4 + (size_t)kMagLen * 2 + 64);
+    if (rc) return rc;
+    uint32_t *d_iq = reinterpret_cast<uint32_t *>(c->d_stage);
+    uint16_t *d_mag = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(c->d_stage) + (size_t)kMaxSamples * 4);
+    if (n)
+        CK(c, cudaMemcpyAsync(d_iq, iq, n * 4, cudaMemcpyHostToDevice, c->stream));
+    to_mag_kernel<<<(kMagLen + 255) / 256, 256, 0, c->stream>>>(d_iq, (int)n, d_mag);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    CK(c, cudaMemcpyAsync(data, d_mag, (size_t)kMagLen * 2, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (length)
+        *length = n;
+    return B200ADSB_OK;
+}
+
+// ------------------------------------------------------------------ device batch
+int b200adsb_scan_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffers, size_t spb,
+                            size_t stride, const uint32_t *d_lengths, uint64_t first_ordinal,
+                            uint64_t ordinal_stride)
+{
+    if (!c || (!d_iq && n_buffers && spb))
+        return B200ADSB_ERR_BAD_ARG;
+    if (stride < spb && n_buffers > 1)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = scan_begin(c, d_iq, false, n_buffers, spb, stride, d_lengths, first_ordinal,
+                    ordinal_stride ? ordinal_stride : 1);
+    if (rc) return rc;
+    rc = scan_run_all(c);
+    if (rc)
+        c->cur.active = false;
+    return rc;
+}
+
+int b200adsb_events_count(b200adsb_ctx *c, size_t *n)
+{
+    if (!c || !n)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = read_counters(c);
+    if (rc) return rc;
+    *n = c->h_counters[C_EV_USED];
+    return B200ADSB_OK;
+}
+
+int b200adsb_events_export_dev(b200adsb_ctx *c, uint64_t *d_pairs, size_t cap, size_t *n)
+{
+    if (!c || (!d_pairs && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    events_export_kernel<<<32, 256, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used, c->d_counters,
+                                                    (unsigned long long *)d_pairs,
+                                                    (uint32_t)std::min<size_t>(cap, 0xffffffffu));
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    rc = read_counters(c);
+    if (rc) return rc;
+    const size_t have = c->h_counters[C_EV_USED];
+    if (n)
+        *n = have;
+    return have > cap ? B200ADSB_ERR_CAPACITY : B200ADSB_OK;
+}
+
+int b200adsb_events_import_dev(b200adsb_ctx *c, const uint64_t *d_pairs, size_t n)
+{
+    if (!c || (!d_pairs && n))
+        return B200ADSB_ERR_BAD_ARG;
+    if (!n)
+        return B200ADSB_OK;
+    int rc = bind(c);
+    if (rc) return rc;
+    events_import_kernel<<<32, 256, 0, c->stream>>>((const unsigned long long *)d_pairs, (uint32_t)n,
+                                                    c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
+                                                    kEvSlots - 1, c->d_counters);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+int b200adsb_resolve_batch_dev(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
+                               uint32_t *d_per_buffer_counts)
+{
+    if (!c || (!d_out && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    return resolve_run(c, d_out, cap, n_out, d_per_buffer_counts);
+}
+
+int b200adsb_demod_iq_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffers, size_t spb,
+                                size_t stride, const uint32_t *d_lengths, b200adsb_frame *d_out,
+                                size_t cap, size_t *n_out, uint32_t *d_per_buffer_counts)
+{
+    if (!c)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = b200adsb_scan_batch_dev(c, d_iq, n_buffers, spb, stride, d_lengths, c->next_ordinal, 1);
+    if (rc) return rc;
+    c->next_ordinal += n_buffers;
+    return resolve_run(c, d_out, cap, n_out, d_per_buffer_counts);
+}
+
+// ------------------------------------------------------------------ host batch
+int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers, size_t spb,
+                            size_t stride, const uint32_t *lengths, b200adsb_frame *out, size_t cap,
+                            size_t *n_out, uint32_t *per_buffer_counts)
+{
+    if (!c || (!iq && n_buffers && spb) || (!out && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    if (spb > (size_t)kMaxSamples || (stride < spb && n_buffers > 1))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    if (n_out)
+        *n_out = 0;
+    // device staging is dense (stride == spb rounded up to 4 samples for 16 B alignment)
+    const size_t dstride = (spb + 3) & ~(size_t)3;
+    const size_t per_pass = std::max<size_t>(1, dstride ? kMaxStageBytes / (dstride * 4 + 4) : n_buffers);
+    size_t done = 0, total_frames = 0;
+    int status = B200ADSB_OK;
+    do {
+        const size_t nb = std::min(per_pass, n_buffers - done);
+        rc = ensure_stage(c, std::max<size_t>(nb * dstride * 4, 16));
+        if (rc) return rc;
+        int16_t *d_iq = reinterpret_cast<int16_t *>(c->d_stage);
+        const uint32_t *d_len = nullptr;
+        if (lengths) {
+            rc = grow(c, &c->d_lengths, &c->lengths_cap, nb);
+            if (rc) return rc;
+            CK(c, cudaMemcpyAsync(c->d_lengths, lengths + done, nb * 4, cudaMemcpyHostToDevice, c->stream));
+            d_len = c->d_lengths;
+        }
+        const size_t room = cap > total_frames ? cap - total_frames : 0;
+        rc = grow(c, &c->d_frames, &c->frames_cap, std::max<size_t>(room, 1));
+        if (rc) return rc;
+        if (per_buffer_counts) {
+            rc = grow(c, &c->d_counts, &c->counts_cap, nb);
+            if (rc) return rc;
+        }
+        rc = scan_begin(c, d_iq, false, nb, spb, dstride, d_len, c->next_ordinal, 1);
+        if (rc) return rc;
+        // H2D in chunks on the copy stream, scan of chunk k overlapping the copy of chunk k+1
+        const size_t chunk = (size_t)c->h2d_chunk;
+        const size_t n_chunks = nb ? (nb + chunk - 1) / chunk : 0;
+        while (c->chunk_events.size() < n_chunks) {
+            cudaEvent_t e;
+            CK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->chunk_events.push_back(e);
+        }
+        rc = reset_scan_counters(c);
+        if (rc) return rc;
+        for (size_t k = 0; k < n_chunks; k++) {
+            const size_t b0 = k * chunk, cb = std::min(chunk, nb - b0);
+            const int16_t *src = iq + 2 * (done + b0) * stride;
+            if (spb) {
+                if (stride == dstride) {
+                    CK(c, cudaMemcpyAsync(d_iq + 2 * b0 * dstride, src, cb * dstride * 4, cudaMemcpyHostToDevice, c->copy_stream));
+                } else {
+                    CK(c, cudaMemcpy2DAsync(d_iq + 2 * b0 * dstride, dstride * 4, src, stride * 4, spb * 4, cb,
+                                            cudaMemcpyHostToDevice, c->copy_stream));
+                }
+            }
+            CK(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
+            CK(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
+            rc = launch_scan(c, (uint32_t)b0, (uint32_t)cb);
+            if (rc) { c->cur.active = false; return rc; }
+        }
+        bool redo = false;
+        rc = check_scan_flags(c, &redo);
+        if (rc) return rc;
+        if (redo) {                      // data is resident now: plain re-run
+            rc = scan_run_all(c);
+            if (rc) { c->cur.active = false; return rc; }
+        }
+        size_t n = 0;
+        rc = resolve_run(c, c->d_frames, room, &n, per_buffer_counts ? c->d_counts : nullptr);
+        if (rc && rc != B200ADSB_ERR_CAPACITY)
+            return rc;
+        if (rc == B200ADSB_ERR_CAPACITY)
+            status = rc;
+        const size_t ncopy = std::min(n, room);
+        if (ncopy)
+            CK(c, cudaMemcpyAsync(out + total_frames, c->d_frames, ncopy * sizeof(b200adsb_frame), cudaMemcpyDeviceToHost, c->stream));
+        if (per_buffer_counts && nb)
+            CK(c, cudaMemcpyAsync(per_buffer_counts + done, c->d_counts, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        // frames carry the buffer index inside this pass: rebase
+        if (done)
+            for (size_t i = 0; i < ncopy; i++)
+                out[total_frames + i].buffer += (uint32_t)done;
+        total_frames += n;
+        c->next_ordinal += nb;
+        done += nb;
+    } while (done < n_buffers);
+    if (n_out)
+        *n_out = total_frames;
+    return status;
+}
+
+int b200adsb_demod_iq(b200adsb_ctx *c, const int16_t *iq, size_t n, b200adsb_frame *out, size_t cap,
+                      size_t *n_out)
+{
+    return b200adsb_demod_iq_batch(c, iq, 1, n, n, nullptr, out, cap, n_out, nullptr);
+}
+
+int b200adsb_demodulate2400(b200adsb_ctx *c, const uint16_t *data, size_t length, b200adsb_frame *out,
+                            size_t cap, size_t *n_out)
+{
+    if (!c || !data || (!out && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    if (length > (size_t)kMaxSamples)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = ensure_stage(c, (size_t)kMagLen * 2 + 64);
+    if (rc) return rc;
+    rc = grow(c, &c->d_frames, &c->frames_cap, std::max<size_t>(cap, 1));
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(c->d_stage, data, (size_t)kMagLen * 2, cudaMemcpyHostToDevice, c->stream));
+    rc = scan_begin(c, c->d_stage, true, 1, length, kMagLen, nullptr, c->next_ordinal, 1);
+    if (rc) return rc;
+    rc = scan_run_all(c);
+    if (rc) { c->cur.active = false; return rc; }
+    c->next_ordinal += 1;
+    size_t n = 0;
+    rc = resolve_run(c, c->d_frames, cap, &n, nullptr);
+    if (rc && rc != B200ADSB_ERR_CAPACITY)
+        return rc;
+    const size_t ncopy = std::min(n, cap);
+    if (ncopy) {
+        CK(c, cudaMemcpyAsync(out, c->d_frames, ncopy * sizeof(b200adsb_frame), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    if (n_out)
+        *n_out = n;
+    return rc;
+}
+
+// ------------------------------------------------------------------ icao_filter.rs
+uint32_t b200adsb_icao_hash(uint32_t a32)   // src/icao_filter.rs:19-43 (pure function)
+{
+    uint64_t a = a32, h = 0;
+    for (int k = 0; k < 3; k++) {
+        h += (a >> (8 * k)) & 0xff;
+        h += h << 10;
+        h ^= h >> 6;
+    }
+    h += h << 3;
+    h ^= h >> 11;
+    h += h << 15;
+    return (uint32_t)h & (B200ADSB_ICAO_FILTER_SIZE - 1);
+}
+
+int b200adsb_icao_flush(b200adsb_ctx *c)
+{
+    if (!c)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    CK(c, cudaMemsetAsync(c->d_members, 0, kMemberSlots * 4, c->stream));
+    CK(c, cudaMemsetAsync(c->d_counters + C_MEMBERS, 0, 4, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B200ADSB_OK;
+}
+
+int b200adsb_icao_filter_add(b200adsb_ctx *c, uint32_t addr)
+{
+    if (!c)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    filter_add_kernel<<<1, 32, 0, c->stream>>>(c->d_members, c->d_counters, addr);
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B200ADSB_OK;
+}
+
+int b200adsb_icao_filter_test(b200adsb_ctx *c, uint32_t addr)
+{
+    if (!c)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    filter_test_kernel<<<1, 32, 0, c->stream>>>(c->d_members, addr, c->d_scalar);
+    CK(c, cudaGetLastError());
+    uint32_t v = 0;
+    CK(c, cudaMemcpyAsync(&v, c->d_scalar, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return (int)v;
+}
+
+int b200adsb_icao_snapshot(b200adsb_ctx *c, uint32_t *keys, size_t cap, size_t *n)
+{
+    if (!c || (!keys && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    std::vector<uint32_t> tab(kMemberSlots);
+    CK(c, cudaMemcpyAsync(tab.data(), c->d_members, kMemberSlots * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    size_t k = 0;
+    for (uint32_t v : tab)
+        if (v) {
+            if (k < cap)
+                keys[k] = v;
+            k++;
+        }
+    if (n)
+        *n = k;
+    return k > cap ? B200ADSB_ERR_CAPACITY : B200ADSB_OK;
+}
+
+int b200adsb_icao_restore(b200adsb_ctx *c, const uint32_t *keys, size_t n)
+{
+    if (!c || (!keys && n) || n > (size_t)B200ADSB_ICAO_FILTER_SIZE)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = b200adsb_icao_flush(c);
+    if (rc) return rc;
+    if (!n)
+        return B200ADSB_OK;
+    CK(c, cudaMemcpyAsync(c->d_new_keys, keys, n * 4, cudaMemcpyHostToDevice, c->stream));
+    filter_restore_kernel<<<1, 1024, 0, c->stream>>>(c->d_members, c->d_counters, c->d_new_keys, (uint32_t)n);
+    CK(c, cudaGetLastError());
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B200ADSB_OK;
+}
+
+// ------------------------------------------------------------------ crc.rs / mode_s
+int b200adsb_modes_checksum(b200adsb_ctx *c, const uint8_t *msgs, size_t n, size_t bits, uint32_t *out)
+{
+    if (!c || (!msgs && n) || (!out && n) || (bits != 56 && bits != 112))
+        return B200ADSB_ERR_BAD_ARG;   // reference asserts n >= 3 bytes (crc.rs:267)
+    if (!n)
+        return B200ADSB_OK;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = ensure_stage(c, n * 14 + n * 4 + 64);
+    if (rc) return rc;
+    uint8_t *d_m = reinterpret_cast<uint8_t *>(c->d_stage);
+    uint32_t *d_o = reinterpret_cast<uint32_t *>(d_m + ((n * 14 + 15) & ~(size_t)15));
+    CK(c, cudaMemcpyAsync(d_m, msgs, n * 14, cudaMemcpyHostToDevice, c->stream));
+    checksum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_m, (int)n, (int)(bits / 8), c->d_crc256, d_o);
+    CK(c, cudaGetLastError());
+    CK(c, cudaMemcpyAsync(out, d_o, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return B200ADSB_OK;
+}
+
+int b200adsb_score_modes_messages(b200adsb_ctx *c, const uint8_t *msgs, size_t n, uint8_t *lens,
+                                  int32_t *scores)
+{
+    if (!c || (!msgs && n) || (!lens && n) || (!scores && n))
+        return B200ADSB_ERR_BAD_ARG;
+    if (!n)
+        return B200ADSB_OK;
+    if (c->cur.active)
+        return B200ADSB_ERR_STATE;
+    int rc = bind(c);
+    if (rc) return rc;
+    const int per_tile = 1024;
+    const size_t n_tiles = (n + per_tile - 1) / per_tile;
+    rc = ensure_stage(c, n * 14 + 64);
+    if (rc) return rc;
+    rc = ensure_pool(c, std::max<size_t>(n, 4096));
+    if (rc) return rc;
+    rc = ensure_tiles(c, n_tiles);
+    if (rc) return rc;
+    rc = grow(c, &c->d_frames, &c->frames_cap, 1);
+    if (rc) return rc;
+    uint8_t *d_m = reinterpret_cast<uint8_t *>(c->d_stage);
+    CK(c, cudaMemcpyAsync(d_m, msgs, n * 14, cudaMemcpyHostToDevice, c->stream));
+    rc = reset_scan_counters(c);
+    if (rc) return rc;
+    classify_msgs_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        d_m, (int)n, c->d_crc256, c->d_rec, c->d_tile_dir, per_tile, c->d_counters, c->d_ev_keys,
+        c->d_ev_ord, c->d_ev_used, kEvSlots - 1, c->next_ordinal);
+    CK(c, cudaGetLastError());
+    rc = read_counters(c);
+    if (rc) return rc;
+    if (c->h_counters[C_FLAGS] & F_EV_OVF) {
+        clear_events(c);
+        return B200ADSB_ERR_EVENTS;
+    }
+    Pending &q = c->cur;
+    q = Pending();
+    q.active = true;
+    q.in = d_m;
+    q.n_buffers = (uint32_t)n_tiles;
+    q.spb = per_tile;
+    q.stride = per_tile;
+    q.T = per_tile;
+    q.tpb = 1;
+    q.n_tiles = (uint32_t)n_tiles;
+    q.ord_first = c->next_ordinal;
+    q.ord_stride = 1;
+    q.msgs = d_m;
+    c->next_ordinal += n_tiles;
+    size_t nf = 0;
+    rc = resolve_run(c, c->d_frames, 0, &nf, nullptr);
+    if (rc && rc != B200ADSB_ERR_CAPACITY)
+        return rc;
+    CK(c, cudaMemcpyAsync(scores, c->d_rec_score, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++) {
+        // MsgLen from the DF bit (mode_s/mod.rs:42-46); None for an all-zero message (:51-53)
+        const uint8_t *m = msgs + 14 * i;
+        bool any = false;
+        for (int k = 0; k < 14; k++)
+            any |= m[k] != 0;
+        lens[i] = !any ? 0 : ((m[0] & 0x80) ? 14 : 7);
+    }
+    return B200ADSB_OK;
+}
+
+/* test hook (pure host): the CRC-24 field tables the scan kernel uses, so that CPU
+ * tests can check them against crc.rs semantics without a GPU.  out: 840 + 256 u32 */
+int b200adsb_debug_crc_tabs(uint32_t *out)
+{
+    if (!out)
+        return B200ADSB_ERR_BAD_ARG;
+    build_crc_tabs(out, out + kTabWords);
+    return kTabWords;
+}
+
+}  // extern "C"

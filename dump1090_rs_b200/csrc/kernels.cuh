@@ -1,0 +1,994 @@
+// dump1090_rs_b200/csrc/kernels.cuh -- device side of libb200adsb (sm_100a).
+//
+// The reference scans one sample at a time on one CPU thread
+// (src/demod_2400.rs:115-212).  Here the same arithmetic is re-organised for a
+// GPU:
+//
+//   scan_kernel (one thread block per tile of T output positions)
+//     P1  IQ -> u16 magnitude into shared memory            (src/utils.rs:43-58)
+//     P2  every sample's five PPM correlator signs and its rising/falling edge
+//         bits, packed by warp ballots into bit planes that are de-interleaved
+//         modulo 12 samples (= one Mode-S bit period at 2.4 Msps is 12/5
+//         samples, so message bit n of try-phase t lives at 1/5-sample position
+//         P = 5(j+19)+t+12n: sample P/5, correlator P%5)  (src/demod_2400.rs:62-83,158-182)
+//     P3  the five preamble templates evaluated 32 positions at a time as AND/shift
+//         of the edge bit planes, then SNR + quiet-zone gates on the survivors
+//                                                          (src/demod_2400.rs:127-146,215-321)
+//     P4  per surviving position and try-phase: five 23-bit field extracts from
+//         the planes, DF, CRC-24 syndrome by table (GF(2)-linear), stateless
+//         classification -> one 24-byte record; ICAO add-events by atomicMin
+//                                                          (src/mode_s/mod.rs:34-139, src/crc.rs:263-282)
+//   finalize/resolve/emit kernels
+//         the sequential ICAO filter (src/icao_filter.rs) evaluated order-free:
+//         member(a) at ordinal o  <=>  a == 0 || a in filter before the batch ||
+//         firstAdd(a) < o; best-of-5 with the reference's strict '>' rule;
+//         frames written in (buffer, j) order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200adsb.h"
+
+namespace b200 {
+
+constexpr int kTrailing = B200ADSB_TRAILING_SAMPLES;          // lib.rs:24
+constexpr int kMaxSamples = B200ADSB_MODES_MAG_BUF_SAMPLES;    // lib.rs:22
+constexpr int kMagLen = B200ADSB_MAG_DATA_LEN;
+constexpr int kHaloFront = 2;    // tile mag index 0 <-> data index tile_start-2 (16 B aligned IQ loads)
+constexpr int kHaloTot = 296;    // mags needed per tile = T + 296 (max tap j+289, +2 front, padded to 8)
+constexpr int kStep = 384;       // 12 residues x 32 lanes: samples per warp step
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxTile = 8192;
+constexpr int kTabWords = 256 + 256 + 64 + 256 + 8;   // CRC-24 field tables (see build_crc_tabs)
+constexpr int kTab56 = 576;
+
+// record word: kind<<29 | key (24 bit, or 1 for the "None" marker)
+enum : uint32_t {
+    K_NONE = 0, K_PAR_SHORT = 1, K_DF11_IID0 = 2, K_DF11_IID = 3, K_DF17 = 4, K_DF18 = 5,
+    K_PAR_LONG = 6
+};
+constexpr uint32_t kNoneMarker = 1;  // kind NONE, key 1: score_modes_message returned None
+
+// counters block (device, u32)
+enum { C_POOL = 0, C_FLAGS = 1, C_EV_USED = 2, C_FRAMES = 3, C_CAND = 4, C_MEMBERS = 5,
+       C_ADMIT = 6, C_NEWCNT = 7, C_WORDS = 16 };
+enum : uint32_t { F_POOL_OVF = 1, F_EV_OVF = 2, F_FILTER_FULL = 4 };
+
+constexpr uint32_t kMemberSlots = 8192;   // open addressing, >= 2 x 4096 keys
+constexpr unsigned long long kNever = ~0ull;
+
+struct ScanParams {
+    const void *in;            // int16 (re,im) pairs, or u16 MagnitudeBuffer.data
+    const uint32_t *lengths;   // nullable per-buffer sample counts
+    uint32_t n_buffers;
+    uint32_t spb;              // samples per buffer (length when lengths == NULL)
+    unsigned long long stride; // IQ: samples between buffers; MAG: u16 elements
+    int T, tiles_per_buffer;
+    int vec_ok;                // 16-byte aligned base and stride % 4 == 0
+    uint32_t *rec;             // pool of 6-word records {j, w[5]}
+    uint32_t pool_cap;
+    uint2 *tile_dir;           // per tile: (pool base, count)
+    uint32_t *counters;
+    uint32_t *ev_keys;
+    unsigned long long *ev_ord;
+    uint32_t *ev_used;
+    uint32_t ev_mask;
+    unsigned long long ord_first, ord_stride;
+    const uint32_t *crc_tabs;
+};
+
+__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// shared memory plan of the scan kernel for tile size T
+struct ScanSmem {
+    int MP, W, WP, nw;
+    size_t off_planes, off_surv, off_tabs, off_cand, bytes;
+    __host__ __device__ explicit ScanSmem(int T)
+    {
+        MP = round_up(T + kHaloTot, kStep);
+        W = MP / kStep;
+        WP = W + 1;
+        nw = (T + 31) / 32;
+        size_t o = (size_t)(MP + 16) * 2;
+        o = (o + 15) & ~(size_t)15;
+        off_planes = o;
+        o += (size_t)7 * 12 * WP * 4;
+        off_surv = o;
+        o += (size_t)nw * 4;
+        off_tabs = o;
+        o += (size_t)kTabWords * 4;
+        off_cand = o;
+        o += (size_t)T * 2;
+        bytes = (o + 15) & ~(size_t)15;
+    }
+};
+
+// ------------------------------------------------------------------ magnitude
+// src/utils.rs:47-55: fi = im/2^15, fq = re/2^15 (exact), fma(fi,fi, rn(fq*fq)),
+// IEEE sqrt, fma(mag, 65535, 0.5), saturating truncation (Rust `as u16`).
+__device__ __forceinline__ uint32_t mag_u16(int re, int im)
+{
+    const float fi = __fmul_rn(__int2float_rn(im), 0x1p-15f);
+    const float fq = __fmul_rn(__int2float_rn(re), 0x1p-15f);
+    const float q2 = __fmul_rn(fq, fq);
+    const float msq = __fmaf_rn(fi, fi, q2);
+    const float mag = __fsqrt_rn(msq);
+    const float v = fminf(__fmaf_rn(mag, 65535.0f, 0.5f), 65535.0f);
+    return __float2uint_rz(v);
+}
+__device__ __forceinline__ uint32_t mag_pair(uint32_t w)  // w = re | im<<16
+{
+    return mag_u16((int)(short)(w & 0xffffu), (int)(short)(w >> 16));
+}
+
+// ------------------------------------------------------------------ CRC-24 by fields
+// Message bit n (MSB first) = 5m + r lives in field r, bit m.  syndrome =
+// sum_n b_n x^(L-1-n) mod G  (src/crc.rs:263-282 is exactly M(x) mod G).
+__device__ __forceinline__ uint32_t mulx(uint32_t s)
+{
+    s <<= 1;
+    return (s & 0x1000000u) ? (s ^ 0x1FFF409u) : s;
+}
+__device__ __forceinline__ uint32_t a112(const uint32_t *t, uint32_t f)
+{
+    return t[f & 0xff] ^ t[256 + ((f >> 8) & 0xff)] ^ t[512 + ((f >> 16) & 0x3f)];
+}
+__device__ __forceinline__ uint32_t a56(const uint32_t *t, uint32_t f)
+{
+    return t[kTab56 + (f & 0xff)] ^ t[kTab56 + 256 + ((f >> 8) & 7)];
+}
+__device__ __forceinline__ uint32_t syn112_fields(const uint32_t *t, const uint32_t f[5])
+{
+    uint32_t s = a112(t, f[0]);
+    s = mulx(s) ^ a112(t, f[1]);
+    s = mulx(s) ^ a112(t, f[2]);
+    s = mulx(s) ^ a112(t, f[3]);
+    s = mulx(s) ^ a112(t, f[4]);
+    return s ^ (((f[0] >> 22) & 1u) << 1) ^ ((f[1] >> 22) & 1u);   // bits 110, 111
+}
+__device__ __forceinline__ uint32_t syn56_fields(const uint32_t *t, const uint32_t f[5])
+{
+    uint32_t s = a56(t, f[0]);
+    s = mulx(s) ^ a56(t, f[1]);
+    s = mulx(s) ^ a56(t, f[2]);
+    s = mulx(s) ^ a56(t, f[3]);
+    s = mulx(s) ^ a56(t, f[4]);
+    return s ^ ((f[0] >> 11) & 1u);                                 // bit 55
+}
+// bits n0 .. n0+cnt-1 of the message, MSB first, from the five fields
+template <int N0, int CNT>
+__device__ __forceinline__ uint32_t msg_bits(const uint32_t f[5])
+{
+    uint32_t v = 0;
+#pragma unroll
+    for (int n = N0; n < N0 + CNT; n++)
+        v = (v << 1) | ((f[n % 5] >> (n / 5)) & 1u);
+    return v;
+}
+
+// src/mode_s/mod.rs:34-139 as a function of the message only
+__device__ __forceinline__ uint32_t classify_fields(const uint32_t *tabs, const uint32_t f[5])
+{
+    if ((f[0] | f[1] | f[2] | f[3] | f[4]) == 0)
+        return kNoneMarker;                      // all 14 bytes zero -> None (:51-53)
+    const uint32_t df = ((f[0] & 1u) << 4) | ((f[1] & 1u) << 3) | ((f[2] & 1u) << 2) |
+                        ((f[3] & 1u) << 1) | (f[4] & 1u);
+    const uint32_t bit = 1u << df;
+    if (bit & 0x00000031u)                       // DF 0,4,5 (:56-72)
+        return (K_PAR_SHORT << 29) | syn56_fields(tabs, f);
+    if (df == 11) {                              // :73-90
+        const uint32_t syn = syn56_fields(tabs, f);
+        if (syn & 0xffff80u)
+            return 0;
+        return (((syn & 0x7f) ? K_DF11_IID : K_DF11_IID0) << 29) | msg_bits<8, 24>(f);
+    }
+    if (bit & 0x00060000u) {                     // DF 17,18 (:91-109)
+        if (syn112_fields(tabs, f) != 0)
+            return 0;
+        return ((df == 17 ? K_DF17 : K_DF18) << 29) | msg_bits<8, 24>(f);
+    }
+    if (bit & 0xFF310000u)                       // DF 16,20,21,24..31 (:110-134)
+        return (K_PAR_LONG << 29) | syn112_fields(tabs, f);
+    return 0;                                    // :135
+}
+
+// byte-wise form for the message-level entry points (crc.rs:263-282 verbatim in spirit)
+__device__ __forceinline__ uint32_t crc_bytes(const uint32_t *tab256, const uint8_t *m, int nbytes)
+{
+    uint32_t rem = 0;
+    for (int i = 0; i < nbytes - 3; i++)
+        rem = ((rem << 8) ^ tab256[m[i] ^ ((rem >> 16) & 0xff)]) & 0xffffffu;
+    return rem ^ ((uint32_t)m[nbytes - 3] << 16) ^ ((uint32_t)m[nbytes - 2] << 8) ^ m[nbytes - 1];
+}
+
+__device__ __forceinline__ uint32_t classify_bytes(const uint32_t *tab256, const uint8_t *m)
+{
+    uint32_t any = 0;
+    for (int i = 0; i < 14; i++)
+        any |= m[i];
+    if (!any)
+        return kNoneMarker;
+    const uint32_t df = m[0] >> 3, bit = 1u << df;
+    const uint32_t addr = ((uint32_t)m[1] << 16) | ((uint32_t)m[2] << 8) | m[3];
+    if (bit & 0x00000031u)
+        return (K_PAR_SHORT << 29) | crc_bytes(tab256, m, 7);
+    if (df == 11) {
+        const uint32_t syn = crc_bytes(tab256, m, 7);
+        if (syn & 0xffff80u)
+            return 0;
+        return (((syn & 0x7f) ? K_DF11_IID : K_DF11_IID0) << 29) | addr;
+    }
+    if (bit & 0x00060000u) {
+        if (crc_bytes(tab256, m, 14) != 0)
+            return 0;
+        return ((df == 17 ? K_DF17 : K_DF18) << 29) | addr;
+    }
+    if (bit & 0xFF310000u)
+        return (K_PAR_LONG << 29) | crc_bytes(tab256, m, 14);
+    return 0;
+}
+
+// ------------------------------------------------------------------ event table
+__device__ __forceinline__ uint32_t hash32(uint32_t k) { return (k * 2654435761u) >> 7; }
+
+// firstAdd(key) = min(firstAdd(key), ord)   
+__device__ inline void event_add(uint32_t *ev_keys, unsigned long long *ev_ord, uint32_t *ev_used,
+                                 uint32_t mask, uint32_t *counters, uint32_t key,
+                                 unsigned long long ord)
+{
+    if ((key & 0xffffffu) == 0 && !(key & B200ADSB_ICAO_FILTER_ADSB_NT))
+        return;   // icao_filter_add(0) stores nothing (icao_filter.rs:58-60)
+    uint32_t h = hash32(key) & mask;
+    for (uint32_t probe = 0; probe <= mask; probe++) {
+        const uint32_t prev = atomicCAS(&ev_keys[h], 0u, key);
+        if (prev == 0u) {
+            const uint32_t u = atomicAdd(&counters[C_EV_USED], 1u);
+            ev_used[u] = h;   // u <= mask because every slot is claimed once
+        }
+        if (prev == 0u || prev == key) {
+            atomicMin(&ev_ord[h], ord);
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+    atomicOr(&counters[C_FLAGS], F_EV_OVF);
+}
+
+__device__ __forceinline__ bool members_has(const uint32_t *members, uint32_t key)
+{
+    uint32_t h = hash32(key) & (kMemberSlots - 1);
+    for (;;) {
+        const uint32_t v = members[h];
+        if (v == key)
+            return true;
+        if (v == 0u)
+            return false;
+        h = (h + 1) & (kMemberSlots - 1);
+    }
+}
+__device__ __forceinline__ void members_insert(uint32_t *members, uint32_t key)
+{
+    uint32_t h = hash32(key) & (kMemberSlots - 1);
+    for (;;) {
+        const uint32_t prev = atomicCAS(&members[h], 0u, key);
+        if (prev == 0u || prev == key)
+            return;
+        h = (h + 1) & (kMemberSlots - 1);
+    }
+}
+__device__ __forceinline__ unsigned long long event_first(const uint32_t *ev_keys,
+                                                          const unsigned long long *ev_ord,
+                                                          uint32_t mask, uint32_t key)
+{
+    uint32_t h = hash32(key) & mask;
+    for (uint32_t probe = 0; probe <= mask; probe++) {
+        const uint32_t v = ev_keys[h];
+        if (v == key)
+            return ev_ord[h];
+        if (v == 0u)
+            return kNever;
+        h = (h + 1) & mask;
+    }
+    return kNever;
+}
+
+// ------------------------------------------------------------------ preamble templates
+// plane[rho][w] bit b  <->  tile mag index 12*(32w+b)+rho.  term(s) returns, for the 32
+// positions of item (rho, w), the plane bit of index position+s.
+__device__ __forceinline__ uint32_t plane_term(const uint32_t *plane, int WP, int rho, int w, int s)
+{
+    int r2 = rho + s;
+    const int c = r2 >= 12;
+    r2 -= 12 * c;
+    const uint32_t *p = plane + r2 * WP + w;
+    return __funnelshift_r(p[0], p[1], c);
+}
+
+// ================================================================== scan kernel
+template <bool FROM_MAG>
+__global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ScanSmem L(p.T);
+    uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
+    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [7][12][WP]
+    uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
+    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
+    uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
+    __shared__ uint32_t s_warp_tot[kWarps];
+    __shared__ uint32_t s_base, s_count, s_ok;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
+    const int k = (int)(tile - b * (uint32_t)p.tiles_per_buffer);
+    const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
+    const int tile_start = k * p.T;
+    if (tile_start >= len) {
+        if (tid == 0)
+            p.tile_dir[tile] = make_uint2(0u, 0u);
+        return;
+    }
+    const int npos = min(p.T, len - tile_start);
+    const int steps = (npos + kHaloTot + kStep - 1) / kStep;   // warp steps actually needed
+    const int MPe = steps * kStep;
+    const int WP = L.WP;
+
+    // ---- P1: magnitudes of tile mag index [0, MPe+16) -> shared memory
+    if (!FROM_MAG) {
+        const int16_t *buf = reinterpret_cast<const int16_t *>(p.in) + 2ull * b * p.stride;
+        const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of mag[0]
+        for (int c = tid; c < (MPe + 16) / 4; c += kThreads) {
+            const int s = s0 + 4 * c;
+            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+            if (s >= 0 && s + 3 < len && p.vec_ok) {
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(buf + 2ll * s));
+                m0 = mag_pair((uint32_t)v.x);
+                m1 = mag_pair((uint32_t)v.y);
+                m2 = mag_pair((uint32_t)v.z);
+                m3 = mag_pair((uint32_t)v.w);
+            } else {
+                const uint32_t *b32 = reinterpret_cast<const uint32_t *>(buf);
+                if (s >= 0 && s < len) m0 = mag_pair(__ldg(b32 + s));
+                if (s + 1 >= 0 && s + 1 < len) m1 = mag_pair(__ldg(b32 + s + 1));
+                if (s + 2 >= 0 && s + 2 < len) m2 = mag_pair(__ldg(b32 + s + 2));
+                if (s + 3 >= 0 && s + 3 < len) m3 = mag_pair(__ldg(b32 + s + 3));
+            }
+            *reinterpret_cast<uint2 *>(mag + 4 * c) = make_uint2(m0 | (m1 << 16), m2 | (m3 << 16));
+        }
+    } else {
+        const uint16_t *d = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
+        const int i0 = tile_start - kHaloFront;   // data index of mag[0]
+        for (int c = tid; c < MPe + 16; c += kThreads) {
+            const int idx = i0 + c;
+            mag[c] = (idx >= 0 && idx < kMagLen) ? __ldg(d + idx) : (uint16_t)0;
+        }
+    }
+    for (int c = tid; c < L.nw; c += kThreads)
+        surv[c] = 0;
+    for (int c = tid; c < kTabWords; c += kThreads)
+        tabs[c] = __ldg(p.crc_tabs + c);
+    for (int c = tid; c < 7 * 12; c += kThreads)
+        planes[c * WP + steps] = 0;   // pad word read by funnel shifts
+    __syncthreads();
+
+    // ---- P2: correlator sign planes S[phi] and edge planes R (rising), F (falling)
+    for (int step = warp; step < steps; step += kWarps) {
+        const uint16_t *mp = mag + kStep * step + 12 * lane;
+        int m[16];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(mp + 4 * q);
+            m[4 * q + 0] = (int)(v.x & 0xffffu);
+            m[4 * q + 1] = (int)(v.x >> 16);
+            m[4 * q + 2] = (int)(v.y & 0xffffu);
+            m[4 * q + 3] = (int)(v.y >> 16);
+        }
+#pragma unroll
+        for (int rho = 0; rho < 12; rho++) {
+            // demod_2400.rs:72-83 written on first differences u,v,w:
+            //   [5,-3,-2]->5u+2v  [4,-1,-3]->4u+3v  [3,1,-4]->3u+4v  [2,3,-5]->2u+5v
+            //   [1,5,-5,-1]->u+6v+w
+            const int u = m[rho] - m[rho + 1], v = m[rho + 1] - m[rho + 2],
+                      w = m[rho + 2] - m[rho + 3];
+            const int g = v - u;
+            const int x0 = 5 * u + 2 * v, x1 = x0 + g, x2 = x1 + g, x3 = x2 + g, x4 = x3 + g + w;
+            const uint32_t b0 = __ballot_sync(0xffffffffu, x0 > 0);
+            const uint32_t b1 = __ballot_sync(0xffffffffu, x1 > 0);
+            const uint32_t b2 = __ballot_sync(0xffffffffu, x2 > 0);
+            const uint32_t b3 = __ballot_sync(0xffffffffu, x3 > 0);
+            const uint32_t b4 = __ballot_sync(0xffffffffu, x4 > 0);
+            const uint32_t br = __ballot_sync(0xffffffffu, u < 0);
+            const uint32_t bf = __ballot_sync(0xffffffffu, u > 0);
+            if (lane == 0) {
+                planes[(0 * 12 + rho) * WP + step] = b0;
+                planes[(1 * 12 + rho) * WP + step] = b1;
+                planes[(2 * 12 + rho) * WP + step] = b2;
+                planes[(3 * 12 + rho) * WP + step] = b3;
+                planes[(4 * 12 + rho) * WP + step] = b4;
+                planes[(5 * 12 + rho) * WP + step] = br;
+                planes[(6 * 12 + rho) * WP + step] = bf;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- P3: preamble templates, 32 positions per item, then the scalar gates
+    {
+        const uint32_t *R = planes + 5 * 12 * WP, *F = planes + 6 * 12 * WP;
+        for (int item = tid; item < 12 * steps; item += kThreads) {
+            const int rho = item / steps, w = item - rho * steps;
+            // valid positions: 2 <= mi < npos+2 with mi = 12*(32w+bit)+rho
+            const int q_lo = (rho < kHaloFront) ? 1 : 0;
+            const int q_hi = (npos + kHaloFront - rho + 11) / 12;   // exclusive
+            int lo = max(q_lo - 32 * w, 0), hi = min(q_hi - 32 * w, 32);
+            if (hi <= lo)
+                continue;
+            uint32_t valid = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            const uint32_t quick = plane_term(R, WP, rho, w, 0) & plane_term(F, WP, rho, w, 12) & valid;
+            if (!quick)
+                continue;
+            const uint32_t F1 = plane_term(F, WP, rho, w, 1), F2 = plane_term(F, WP, rho, w, 2),
+                           F3 = plane_term(F, WP, rho, w, 3), F4 = plane_term(F, WP, rho, w, 4),
+                           F9 = plane_term(F, WP, rho, w, 9), F10 = plane_term(F, WP, rho, w, 10);
+            const uint32_t R2 = plane_term(R, WP, rho, w, 2), R3 = plane_term(R, WP, rho, w, 3),
+                           R8 = plane_term(R, WP, rho, w, 8), R9 = plane_term(R, WP, rho, w, 9),
+                           R10 = plane_term(R, WP, rho, w, 10), R11 = plane_term(R, WP, rho, w, 11);
+            // demod_2400.rs:226-317, in order
+            const uint32_t T3 = F1 & R2 & F3 & R8 & F9 & R10;
+            const uint32_t T4 = F1 & R2 & F3 & R8 & F9 & R11;
+            const uint32_t T5 = F1 & R2 & F4 & R8 & F10 & R11;
+            const uint32_t T6 = F1 & R3 & F4 & R9 & F10 & R11;
+            const uint32_t T7 = F2 & R3 & F4 & R9 & F10 & R11;
+            uint32_t any = quick & (T3 | T4 | T5 | T6 | T7);
+            while (any) {
+                const int bit = __ffs(any) - 1;
+                any &= any - 1;
+                const int mi = 12 * (32 * w + bit) + rho;
+                const uint16_t *pp = mag + mi;
+                int high;
+                uint32_t sig, noise;
+                if ((T3 >> bit) & 1u) {
+                    high = ((int)pp[1] + pp[3] + pp[9] + pp[11] + pp[12]) / 4;
+                    sig = (uint32_t)pp[1] + pp[3] + pp[9];
+                    noise = (uint32_t)pp[5] + pp[6] + pp[7];
+                } else if ((T4 >> bit) & 1u) {
+                    high = ((int)pp[1] + pp[3] + pp[9] + pp[12]) / 4;
+                    sig = (uint32_t)pp[1] + pp[3] + pp[9] + pp[12];
+                    noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
+                } else if ((T5 >> bit) & 1u) {
+                    high = ((int)pp[1] + pp[3] + pp[4] + pp[9] + pp[10] + pp[12]) / 4;
+                    sig = (uint32_t)pp[1] + pp[12];
+                    noise = (uint32_t)pp[6] + pp[7];
+                } else if ((T6 >> bit) & 1u) {
+                    high = ((int)pp[1] + pp[4] + pp[10] + pp[12]) / 4;
+                    sig = (uint32_t)pp[1] + pp[4] + pp[10] + pp[12];
+                    noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
+                } else {
+                    high = ((int)pp[1] + pp[2] + pp[4] + pp[10] + pp[12]) / 4;
+                    sig = (uint32_t)pp[4] + pp[10] + pp[12];
+                    noise = (uint32_t)pp[6] + pp[7] + pp[8];
+                }
+                if (sig * 2 < 3 * noise)   // demod_2400.rs:129
+                    continue;
+                // demod_2400.rs:135-146
+                const int mx = max(max(max((int)pp[5], (int)pp[6]), max((int)pp[7], (int)pp[8])),
+                                   max(max(max((int)pp[14], (int)pp[15]), max((int)pp[16], (int)pp[17])),
+                                       (int)pp[18]));
+                if (mx >= high)
+                    continue;
+                const int jl = mi - kHaloFront;
+                atomicOr(&surv[jl >> 5], 1u << (jl & 31));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- P4a: ordered list of surviving positions (ascending j)
+    {
+        uint32_t wv = (tid < L.nw) ? surv[tid] : 0u;   // nw <= 256 == kThreads
+        const int cnt = __popc(wv);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_warp_tot[warp] = (uint32_t)incl;
+        __syncthreads();
+        int off = incl - cnt;
+        uint32_t total = 0;
+#pragma unroll
+        for (int wi = 0; wi < kWarps; wi++) {
+            const uint32_t t = s_warp_tot[wi];
+            if (wi < warp)
+                off += (int)t;
+            total += t;
+        }
+        while (wv) {
+            const int bit = __ffs(wv) - 1;
+            wv &= wv - 1;
+            cand[off++] = (uint16_t)(tid * 32 + bit);
+        }
+        if (tid == 0) {
+            uint32_t base = 0, ok = 1;
+            if (total) {
+                base = atomicAdd(&p.counters[C_POOL], total);
+                if (base + total > p.pool_cap || base + total < base) {
+                    atomicOr(&p.counters[C_FLAGS], F_POOL_OVF);
+                    ok = 0;
+                }
+                atomicAdd(&p.counters[C_CAND], total);
+            }
+            p.tile_dir[tile] = make_uint2(base, ok ? total : 0u);
+            s_base = base;
+            s_count = total;
+            s_ok = ok;
+        }
+    }
+    __syncthreads();
+    if (!s_ok || s_count == 0)
+        return;
+
+    // ---- P4b: five try-phases per survivor -> record words + ICAO add-events
+    {
+        const int C = (int)s_count;
+        const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
+        for (int item = tid; item < 5 * C; item += kThreads) {
+            const int c = item / 5, tt = item - 5 * c;
+            const int jl = cand[c];
+            const int P0 = 5 * (jl + kHaloFront + 19) + 4 + tt;   // demod_2400.rs:158-160
+            uint32_t f[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const int Pr = P0 + 12 * r;
+                const int i = Pr / 5, phi = Pr - 5 * i;
+                const int q = i / 12, rho = i - 12 * q;
+                const uint32_t *st = planes + (phi * 12 + rho) * WP + (q >> 5);
+                f[r] = __funnelshift_r(st[0], st[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
+            }
+            const uint32_t wd = classify_fields(tabs, f);
+            const uint32_t kind = wd >> 29;
+            const uint32_t j = (uint32_t)(tile_start + jl);
+            uint32_t *rec = p.rec + 6ull * (s_base + (uint32_t)c);
+            rec[1 + tt] = wd;
+            if (tt == 0)
+                rec[0] = j;
+            if (kind == K_DF11_IID0 || kind == K_DF17 || kind == K_DF18) {
+                const uint32_t key = (wd & 0xffffffu) | (kind == K_DF18 ? B200ADSB_ICAO_FILTER_ADSB_NT : 0u);
+                event_add(p.ev_keys, p.ev_ord, p.ev_used, p.ev_mask, p.counters, key,
+                          ord_buf | ((unsigned long long)j << 3) | (unsigned long long)tt);
+            }
+        }
+    }
+}
+
+// ================================================================== to_mag kernel
+// utils::to_mag (src/utils.rs:43-58) with the MagnitudeBuffer layout of src/lib.rs:29-51
+__global__ void to_mag_kernel(const uint32_t *__restrict__ iq, int n, uint16_t *__restrict__ data)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= kMagLen)
+        return;
+    const int s = i - kTrailing;
+    data[i] = (s >= 0 && s < n) ? (uint16_t)mag_pair(__ldg(iq + s)) : (uint16_t)0;
+}
+
+// ================================================================== message-level kernels
+__global__ void checksum_kernel(const uint8_t *__restrict__ msgs, int n, int nbytes,
+                                const uint32_t *__restrict__ tab256, uint32_t *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = crc_bytes(tab256, msgs + 14ll * i, nbytes);
+}
+
+// one record per message (w[0] only), tile_dir describing "tiles" of 1024 messages
+__global__ void classify_msgs_kernel(const uint8_t *__restrict__ msgs, int n,
+                                     const uint32_t *__restrict__ tab256, uint32_t *rec,
+                                     uint2 *tile_dir, int per_tile, uint32_t *counters,
+                                     uint32_t *ev_keys, unsigned long long *ev_ord, uint32_t *ev_used,
+                                     uint32_t ev_mask, unsigned long long ord_first)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t wd = classify_bytes(tab256, msgs + 14ll * i);
+        uint32_t *r = rec + 6ull * i;
+        r[0] = (uint32_t)(i % per_tile);
+        r[1] = wd;
+        r[2] = r[3] = r[4] = r[5] = 0;
+        const uint32_t kind = wd >> 29;
+        if (kind == K_DF11_IID0 || kind == K_DF17 || kind == K_DF18) {
+            const uint32_t key = (wd & 0xffffffu) | (kind == K_DF18 ? B200ADSB_ICAO_FILTER_ADSB_NT : 0u);
+            const unsigned long long ord =
+                ((ord_first + (unsigned long long)(i / per_tile)) << 20) |
+                ((unsigned long long)(i % per_tile) << 3);
+            event_add(ev_keys, ev_ord, ev_used, ev_mask, counters, key, ord);
+        }
+        if (i % per_tile == 0)
+            tile_dir[i / per_tile] = make_uint2((uint32_t)i, (uint32_t)min(per_tile, n - i));
+    }
+}
+
+// ================================================================== events
+// export (key, ord) pairs of the slots used by this rank
+__global__ void events_export_kernel(const uint32_t *ev_keys, const unsigned long long *ev_ord,
+                                     const uint32_t *ev_used, const uint32_t *counters,
+                                     unsigned long long *pairs, uint32_t cap)
+{
+    const uint32_t n = min(counters[C_EV_USED], cap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t h = ev_used[i];
+        pairs[2ull * i] = ev_keys[h];
+        pairs[2ull * i + 1] = ev_ord[h];
+    }
+}
+__global__ void events_import_kernel(const unsigned long long *pairs, uint32_t n, uint32_t *ev_keys,
+                                     unsigned long long *ev_ord, uint32_t *ev_used, uint32_t mask,
+                                     uint32_t *counters)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        event_add(ev_keys, ev_ord, ev_used, mask, counters, (uint32_t)pairs[2ull * i], pairs[2ull * i + 1]);
+}
+
+// Capacity rule of icao_filter_add (src/icao_filter.rs:46-62): the table holds the
+// first 4096 distinct keys by first-add order; later ones are dropped.  One block.
+__global__ void __launch_bounds__(1024) events_finalize_kernel(
+    const uint32_t *ev_keys, unsigned long long *ev_ord, const uint32_t *ev_used, uint32_t *ev_tmp,
+    uint32_t *new_keys, uint32_t *counters, const uint32_t *members)
+{
+    const uint32_t n = counters[C_EV_USED];
+    const uint32_t have = counters[C_MEMBERS];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t h = ev_used[i];
+        ev_tmp[i] = members_has(members, ev_keys[h]) ? 0u : 1u;
+    }
+    __syncthreads();
+    uint32_t my_new = 0;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        if (!ev_tmp[i])
+            continue;   // already a member: add is a no-op, membership comes from the table
+        my_new++;
+        const unsigned long long ord = ev_ord[ev_used[i]];
+        uint32_t rank = 0;
+        for (uint32_t k = 0; k < n; k++)
+            rank += (ev_tmp[k] && ev_ord[ev_used[k]] < ord) ? 1u : 0u;
+        // ordinals of distinct keys can tie only if (buffer, j, phase) coincide, which
+        // cannot happen: one decode adds at most one key.
+        if (have + rank < (uint32_t)B200ADSB_ICAO_FILTER_SIZE)
+            new_keys[rank] = ev_keys[ev_used[i]];
+        else
+            ev_tmp[i] = 2u;   // dropped: "icao24 hash table full"
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (ev_tmp[i] == 2u)
+            ev_ord[ev_used[i]] = kNever;
+    atomicAdd(&counters[C_NEWCNT], my_new);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t nn = counters[C_NEWCNT];
+        const uint32_t room = (uint32_t)B200ADSB_ICAO_FILTER_SIZE - have;
+        counters[C_ADMIT] = min(nn, room);
+        if (nn > room)
+            atomicOr(&counters[C_FLAGS], F_FILTER_FULL);
+    }
+}
+
+// after resolve: the admitted keys join the filter; the event table is recycled
+__global__ void __launch_bounds__(1024) events_commit_kernel(
+    uint32_t *ev_keys, unsigned long long *ev_ord, const uint32_t *ev_used, const uint32_t *new_keys,
+    uint32_t *counters, uint32_t *members)
+{
+    const uint32_t n = counters[C_EV_USED], adm = counters[C_ADMIT];
+    for (uint32_t i = threadIdx.x; i < adm; i += blockDim.x)
+        members_insert(members, new_keys[i]);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t h = ev_used[i];
+        ev_keys[h] = 0u;
+        ev_ord[h] = kNever;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        counters[C_MEMBERS] += adm;
+        counters[C_EV_USED] = 0;
+        counters[C_ADMIT] = 0;
+        counters[C_NEWCNT] = 0;
+    }
+}
+
+// ================================================================== resolve
+struct ResolveParams {
+    const uint32_t *rec;
+    const uint2 *tile_dir;
+    uint32_t n_tiles;
+    int tiles_per_buffer;
+    uint32_t *emit_info;       // per record: 0, or score<<16 | len<<8 | phase
+    uint32_t *tile_emit;       // per tile: frames emitted
+    int32_t *rec_score;        // nullable: per record best score (diagnostics / message API)
+    const uint32_t *members;
+    const uint32_t *ev_keys;
+    const unsigned long long *ev_ord;
+    uint32_t ev_mask;
+    unsigned long long ord_first, ord_stride;
+};
+
+__device__ __forceinline__ bool is_member(const ResolveParams &p, uint32_t key, unsigned long long ord)
+{
+    if (key == 0u)
+        return true;                         // icao_filter_test(0) (icao_filter.rs:71,78)
+    if (members_has(p.members, key))
+        return true;
+    return event_first(p.ev_keys, p.ev_ord, p.ev_mask, key) < ord;
+}
+
+// one warp per tile; lanes stride over the tile's records
+__global__ void __launch_bounds__(kThreads) resolve_kernel(const ResolveParams p)
+{
+    const uint32_t tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (tile >= p.n_tiles)
+        return;
+    const uint2 d = p.tile_dir[tile];
+    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
+    const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
+    uint32_t emitted = 0;
+    for (uint32_t i = lane; i < d.y; i += 32) {
+        const uint32_t *r = p.rec + 6ull * (d.x + i);
+        const uint32_t j = r[0];
+        int best = -2;                        // demod_2400.rs:152
+        uint32_t best_t = 0, best_len = 7;
+#pragma unroll
+        for (int tt = 0; tt < 5; tt++) {
+            const uint32_t wd = r[1 + tt];
+            const uint32_t kind = wd >> 29, key = wd & 0xffffffu;
+            if (kind == K_NONE)
+                continue;
+            const bool m = is_member(p, key, ord_buf | ((unsigned long long)j << 3) | (unsigned)tt);
+            int score;
+            uint32_t len;
+            switch (kind) {                   // mode_s/mod.rs:56-134
+            case K_PAR_SHORT: score = m ? 1000 : -1; len = 7; break;
+            case K_DF11_IID0: score = m ? 1600 : 750; len = 7; break;
+            case K_DF11_IID: score = m ? 1000 : -1; len = 7; break;
+            case K_DF17:
+            case K_DF18: score = m ? 1800 : 1400; len = 14; break;
+            default: score = m ? 1000 : -2; len = 14; break;
+            }
+            if (score > best) {               // demod_2400.rs:185 (strict)
+                best = score;
+                best_t = (uint32_t)tt;
+                best_len = len;
+            }
+        }
+        const bool emit = best >= 0;          // demod_2400.rs:203
+        p.emit_info[d.x + i] = emit ? (((uint32_t)best << 16) | (best_len << 8) | (4u + best_t)) : 0u;
+        if (p.rec_score)
+            p.rec_score[d.x + i] = best;
+        emitted += emit ? 1u : 0u;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+        emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
+    if (lane == 0)
+        p.tile_emit[tile] = emitted;
+}
+
+// exclusive scan of tile_emit (in place) by one block; total -> counters[C_FRAMES];
+// per-buffer counts optional
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t *tile_emit, uint32_t n_tiles,
+                                                         uint32_t *counters)
+{
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0)
+        s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_tiles ? tile_emit[i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t x = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o)
+                    x += t;
+            }
+            s_w[lane] = x;
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        const uint32_t excl = carry + (warp ? s_w[warp - 1] : 0u) + incl - v;
+        if (i < n_tiles)
+            tile_emit[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023)
+            s_carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        counters[C_FRAMES] = s_carry;
+}
+
+__global__ void buffer_counts_kernel(const uint32_t *tile_excl, uint32_t n_buffers, int tpb,
+                                     uint32_t n_tiles, const uint32_t *counters, uint32_t *out)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_buffers)
+        return;
+    const uint32_t lo = tile_excl[(size_t)b * tpb];
+    const uint32_t nx = (b + 1) * (uint32_t)tpb;
+    const uint32_t hi = nx < n_tiles ? tile_excl[nx] : counters[C_FRAMES];
+    out[b] = hi - lo;
+}
+
+// ================================================================== emit
+struct EmitParams {
+    const void *in;
+    const uint32_t *lengths;
+    uint32_t spb;
+    unsigned long long stride;
+    const uint32_t *rec;
+    const uint2 *tile_dir;
+    const uint32_t *emit_info;
+    const uint32_t *tile_excl;
+    uint32_t n_tiles;
+    int tiles_per_buffer;
+    b200adsb_frame *out;
+    uint32_t cap;
+    const uint8_t *msgs;   // message-level API: frames copy their bytes from here
+};
+
+// one warp per tile; every emitted frame is re-sliced from the input by the whole warp
+// (src/demod_2400.rs:158-182 in closed form: bit n of try_phase t is decided at
+//  P = 5(j+19)+t+12n, sample P/5, correlator P%5)
+template <bool FROM_MAG>
+__global__ void __launch_bounds__(kThreads) emit_kernel(const EmitParams p)
+{
+    __shared__ uint16_t s_mag[kWarps][288];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * kWarps + warp;
+    if (tile >= p.n_tiles)
+        return;
+    const uint2 d = p.tile_dir[tile];
+    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
+    uint32_t out_idx = p.tile_excl[tile];
+    const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
+    for (uint32_t base = 0; base < d.y; base += 32) {
+        const uint32_t i = base + lane;
+        const uint32_t info = i < d.y ? p.emit_info[d.x + i] : 0u;
+        const uint32_t jmine = (i < d.y && info) ? p.rec[6ull * (d.x + i)] : 0u;
+        uint32_t mask = __ballot_sync(0xffffffffu, info != 0u);
+        while (mask) {
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const uint32_t inf = __shfl_sync(0xffffffffu, info, src);
+            const uint32_t j = __shfl_sync(0xffffffffu, jmine, src);
+            const int t = (int)(inf & 0xff), flen = (int)((inf >> 8) & 0xff);
+            uint32_t words[4] = {0, 0, 0, 0};
+            if (p.msgs == nullptr) {
+                // magnitudes of data[j+19 .. j+19+288)
+                for (int k = lane; k < 288; k += 32) {
+                    const int idx = (int)j + 19 + k;
+                    uint32_t m = 0;
+                    if (FROM_MAG) {
+                        const uint16_t *dd = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
+                        if (idx < kMagLen)
+                            m = dd[idx];
+                    } else {
+                        const uint32_t *bb = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
+                        const int s = idx - kTrailing;
+                        if (s >= 0 && s < len)
+                            m = mag_pair(__ldg(bb + s));
+                    }
+                    s_mag[warp][k] = (uint16_t)m;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int wi = 0; wi < 4; wi++) {
+                    const int n = 32 * wi + lane;
+                    bool one = false;
+                    if (n < 112) {
+                        const int P = t + 12 * n;          // relative to 5*(j+19)
+                        const int i5 = P / 5, phi = P - 5 * i5;
+                        const uint16_t *m = &s_mag[warp][i5];
+                        const int m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+                        int x;
+                        switch (phi) {                      // demod_2400.rs:72-83
+                        case 0: x = 5 * m0 - 3 * m1 - 2 * m2; break;
+                        case 1: x = 4 * m0 - m1 - 3 * m2; break;
+                        case 2: x = 3 * m0 + m1 - 4 * m2; break;
+                        case 3: x = 2 * m0 + 3 * m1 - 5 * m2; break;
+                        default: x = m0 + 5 * m1 - 5 * m2 - m3; break;
+                        }
+                        one = x > 0;
+                    }
+                    words[wi] = __ballot_sync(0xffffffffu, one);
+                }
+                __syncwarp();
+            }
+            if (out_idx < p.cap) {
+                // frame = 7 u32 words: msg[0..13], len, phase | score, reserved | j | buffer
+                uint8_t by[16];
+#pragma unroll
+                for (int kb = 0; kb < 14; kb++) {
+                    uint32_t v;
+                    if (p.msgs)
+                        v = p.msgs[14ull * ((unsigned long long)b * 1024ull + j) + kb];
+                    else
+                        v = __brev((words[kb >> 2] >> (8 * (kb & 3))) & 0xffu) >> 24;
+                    by[kb] = (kb < flen) ? (uint8_t)v : (uint8_t)0;
+                }
+                by[14] = (uint8_t)flen;
+                by[15] = (uint8_t)t;
+                if (lane == 0) {
+                    uint32_t *o = reinterpret_cast<uint32_t *>(p.out + out_idx);
+#pragma unroll
+                    for (int wq = 0; wq < 4; wq++)
+                        o[wq] = by[4 * wq] | (by[4 * wq + 1] << 8) | (by[4 * wq + 2] << 16) |
+                                ((uint32_t)by[4 * wq + 3] << 24);
+                    o[4] = (inf >> 16) & 0xffffu;   // score (>= 0 here), reserved = 0
+                    o[5] = j;
+                    o[6] = b;
+                }
+            }
+            out_idx++;
+        }
+    }
+}
+
+// ================================================================== filter helpers
+__global__ void filter_add_kernel(uint32_t *members, uint32_t *counters, uint32_t key)
+{
+    if (threadIdx.x || blockIdx.x)
+        return;
+    if (key == 0u || members_has(members, key))
+        return;
+    if (counters[C_MEMBERS] >= (uint32_t)B200ADSB_ICAO_FILTER_SIZE) {
+        atomicOr(&counters[C_FLAGS], F_FILTER_FULL);
+        return;
+    }
+    members_insert(members, key);
+    counters[C_MEMBERS] += 1;
+}
+__global__ void filter_test_kernel(const uint32_t *members, uint32_t key, uint32_t *out)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+        *out = (key == 0u || members_has(members, key)) ? 1u : 0u;
+}
+__global__ void filter_restore_kernel(uint32_t *members, uint32_t *counters, const uint32_t *keys,
+                                      uint32_t n)
+{
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        if (keys[i])
+            members_insert(members, keys[i]);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t c = 0;
+        for (uint32_t h = 0; h < kMemberSlots; h++)
+            c += members[h] != 0u;
+        counters[C_MEMBERS] = c;
+    }
+}
+__global__ void fill_u64_kernel(unsigned long long *p, size_t n, unsigned long long v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+}  // namespace b200

@@ -1,0 +1,188 @@
+/*
+ * include/b200adsb.h -- C ABI of libb200adsb.so, the B200-native (sm_100a CUDA)
+ * replacement of the dump1090_rs demodulation hot path
+ *
+ *     CS16 IQ -> magnitude -> 8 us preamble gate -> 5-phase PPM bit slicing
+ *             -> Mode-S CRC-24 / scoring -> 56/112-bit frames
+ *
+ * Each entry point names the reference interface it replaces (file:line in
+ * rsadsb/dump1090_rs @ 94a0e4d).  Plain pointers and sizes only; no C++ or
+ * torch types cross this boundary.  Every function returns a status code
+ * (B200ADSB_OK == 0, negative on error) and never aborts or unwinds.
+ *
+ * Threading: one context == one ordered stream of buffers with one ICAO
+ * address filter (the reference's process-wide tables, src/icao_filter.rs:8-9).
+ * Calls on one context must be serialised by the caller; contexts are
+ * independent.  Results are ordered by (buffer, j) exactly like the reference's
+ * Vec<ModeSMessage> (src/demod_2400.rs:121,207).
+ *
+ * There is no CPU fallback: every call that computes runs CUDA kernels on the
+ * context's device and fails with B200ADSB_ERR_CUDA if that is impossible.
+ */
+#ifndef B200ADSB_H
+#define B200ADSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* src/lib.rs:22-26 */
+#define B200ADSB_MODES_MAG_BUF_SAMPLES 131072
+#define B200ADSB_TRAILING_SAMPLES 326
+#define B200ADSB_MAG_DATA_LEN (B200ADSB_TRAILING_SAMPLES + B200ADSB_MODES_MAG_BUF_SAMPLES)
+#define B200ADSB_MODES_LONG_MSG_BYTES 14
+#define B200ADSB_MODES_SHORT_MSG_BYTES 7
+/* src/icao_filter.rs:5-6 */
+#define B200ADSB_ICAO_FILTER_SIZE 4096
+#define B200ADSB_ICAO_FILTER_ADSB_NT (1u << 25)
+
+enum {
+    B200ADSB_OK = 0,
+    B200ADSB_ERR_BAD_ARG = -1,   /* null pointer, n > 131072 (reference panics, lib.rs:48), ... */
+    B200ADSB_ERR_CAPACITY = -2,  /* caller's output array too small; *n_out holds the need   */
+    B200ADSB_ERR_CUDA = -3,      /* CUDA runtime error; see b200adsb_last_error()             */
+    B200ADSB_ERR_NOMEM = -4,
+    B200ADSB_ERR_STATE = -5,     /* calls out of order (resolve before scan, ...)             */
+    B200ADSB_ERR_EVENTS = -6     /* more distinct new addresses in one batch than event slots */
+};
+
+/* context options (b200adsb_ctx_set_option) */
+enum {
+    B200ADSB_OPT_TILE = 1,        /* output positions per thread block tile (multiple of 32) */
+    B200ADSB_OPT_POOL_SHIFT = 2,  /* candidate pool = positions >> shift (grown on demand)    */
+    B200ADSB_OPT_PROFILE = 3,     /* 1: bracket kernels with CUDA events (b200adsb_timing)    */
+    B200ADSB_OPT_H2D_CHUNK = 4    /* buffers per host->device pipeline chunk (host batch API) */
+};
+
+typedef struct b200adsb_ctx b200adsb_ctx;
+
+/* One decoded frame: what ModeSMessage exposes through buffer()
+ * (src/demod_2400.rs:93-112) plus where it was found.  28 bytes. */
+typedef struct {
+    uint8_t msg[B200ADSB_MODES_LONG_MSG_BYTES]; /* msg[..len] == ModeSMessage::buffer() */
+    uint8_t len;        /* 7 (MsgLen::Short) or 14 (MsgLen::Long)                        */
+    uint8_t phase;      /* winning try_phase, 4..8 (private in the reference)            */
+    int16_t score;      /* score_modes_message value of the winner (private there)       */
+    uint16_t reserved;
+    uint32_t j;         /* index into MagnitudeBuffer.data where the preamble starts     */
+    uint32_t buffer;    /* index of the IQ buffer inside the batch                       */
+} b200adsb_frame;
+
+/* accumulated device time per stage since the last reset (OPT_PROFILE=1) */
+typedef struct {
+    double scan_ms;     /* fused magnitude+preamble+slice+CRC kernel                     */
+    double resolve_ms;  /* event finalise + filter resolve + ordered emit                */
+    double h2d_ms, d2h_ms;
+    uint64_t scan_launches, other_launches;
+    uint64_t samples;   /* IQ samples pushed through the scan kernel                     */
+    uint64_t candidates;/* positions that passed all preamble gates                      */
+} b200adsb_timing;
+
+/* ------------------------------------------------------------------ life cycle */
+int b200adsb_version(void);
+const char *b200adsb_strerror(int status);
+const char *b200adsb_last_error(const b200adsb_ctx *ctx); /* last CUDA error text */
+
+/* device: CUDA ordinal.  stream: a cudaStream_t to launch on (e.g. torch's
+ * current stream) or NULL for a private non-blocking stream. */
+int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream);
+void b200adsb_ctx_destroy(b200adsb_ctx *ctx);
+int b200adsb_ctx_set_option(b200adsb_ctx *ctx, int option, int64_t value);
+int b200adsb_ctx_sync(b200adsb_ctx *ctx);
+int b200adsb_timing_get(b200adsb_ctx *ctx, b200adsb_timing *out, int reset);
+
+/* pinned host memory for the host-buffer entry points (plain malloc'd memory
+ * works too, only slower) */
+void *b200adsb_host_alloc(size_t bytes);
+void b200adsb_host_free(void *p);
+
+/* ------------------------------------------------ reference surface, one buffer */
+
+/* utils::to_mag(&[Complex<i16>]) -> MagnitudeBuffer        (src/utils.rs:43-58)
+ * iq_re_im: n interleaved (re, im) int16 pairs in memory order (host memory).
+ * data: host array of B200ADSB_MAG_DATA_LEN u16 (MagnitudeBuffer.data,
+ * src/lib.rs:31); data[0..326) = 0, data[326+k] = magnitude of sample k,
+ * the rest 0 (MagnitudeBuffer::default, lib.rs:36-44).  *length = n. */
+int b200adsb_to_mag(b200adsb_ctx *ctx, const int16_t *iq_re_im, size_t n, uint16_t *data,
+                    size_t *length);
+
+/* demod_2400::demodulate2400(&MagnitudeBuffer) -> Vec<ModeSMessage>
+ *                                                          (src/demod_2400.rs:115-212)
+ * data/length: a MagnitudeBuffer (host).  Uses and updates the context filter. */
+int b200adsb_demodulate2400(b200adsb_ctx *ctx, const uint16_t *data, size_t length,
+                            b200adsb_frame *out, size_t cap, size_t *n_out);
+
+/* to_mag + demodulate2400 fused (the pair every caller issues: main.rs:166-167,
+ * tests/test.rs:11-13, benches/demod_benchmark.rs:10-11); the magnitude never
+ * leaves the chip. */
+int b200adsb_demod_iq(b200adsb_ctx *ctx, const int16_t *iq_re_im, size_t n,
+                      b200adsb_frame *out, size_t cap, size_t *n_out);
+
+/* --------------------------------------------------------------- batched stream */
+
+/* n_buffers consecutive buffers of one stream (buffer b starts at
+ * iq + 2*b*stride_samples int16, has samples_per_buffer samples, or lengths[b]
+ * if lengths != NULL), processed as the reference would process them one after
+ * the other with one filter.  Host pointers; H2D/D2H are pipelined inside.
+ * per_buffer_counts (nullable, host): frames found in each buffer. */
+int b200adsb_demod_iq_batch(b200adsb_ctx *ctx, const int16_t *iq_re_im, size_t n_buffers,
+                            size_t samples_per_buffer, size_t stride_samples,
+                            const uint32_t *lengths, b200adsb_frame *out, size_t cap,
+                            size_t *n_out, uint32_t *per_buffer_counts);
+
+/* Same with the IQ already resident in device memory (d_iq) and frames left in
+ * device memory (d_out, cap entries); *n_out is read back.  d_lengths nullable
+ * (device).  d_per_buffer_counts nullable (device, n_buffers u32). */
+int b200adsb_demod_iq_batch_dev(b200adsb_ctx *ctx, const int16_t *d_iq, size_t n_buffers,
+                                size_t samples_per_buffer, size_t stride_samples,
+                                const uint32_t *d_lengths, b200adsb_frame *d_out, size_t cap,
+                                size_t *n_out, uint32_t *d_per_buffer_counts);
+
+/* ---- split form for a stream sharded over several GPUs (one context per rank).
+ * scan:    stage 1 on this rank's buffers; local buffer b has stream ordinal
+ *          first_ordinal + b*ordinal_stride (round robin: first=rank, stride=world).
+ * events:  the ICAO add-events (key, first ordinal) this rank saw -- a few per
+ *          buffer -- to be all-gathered between ranks and imported everywhere.
+ * resolve: stage 2, identical filter evolution on every rank.               */
+int b200adsb_scan_batch_dev(b200adsb_ctx *ctx, const int16_t *d_iq, size_t n_buffers,
+                            size_t samples_per_buffer, size_t stride_samples,
+                            const uint32_t *d_lengths, uint64_t first_ordinal,
+                            uint64_t ordinal_stride);
+int b200adsb_events_count(b200adsb_ctx *ctx, size_t *n);
+/* pairs: 2*cap u64 in DEVICE memory: (key, ordinal) per event */
+int b200adsb_events_export_dev(b200adsb_ctx *ctx, uint64_t *d_pairs, size_t cap, size_t *n);
+int b200adsb_events_import_dev(b200adsb_ctx *ctx, const uint64_t *d_pairs, size_t n);
+int b200adsb_resolve_batch_dev(b200adsb_ctx *ctx, b200adsb_frame *d_out, size_t cap,
+                               size_t *n_out, uint32_t *d_per_buffer_counts);
+
+/* --------------------------------------------------------------- icao_filter.rs */
+int b200adsb_icao_flush(b200adsb_ctx *ctx);                    /* icao_flush       :11-17 */
+uint32_t b200adsb_icao_hash(uint32_t a);                       /* icao_hash        :19-43 */
+int b200adsb_icao_filter_add(b200adsb_ctx *ctx, uint32_t addr);/* icao_filter_add  :46-62 */
+int b200adsb_icao_filter_test(b200adsb_ctx *ctx, uint32_t addr);/* icao_filter_test :65-97; 1/0 */
+/* checkpoint / resume of the filter (the reference keeps it in RAM only) */
+int b200adsb_icao_snapshot(b200adsb_ctx *ctx, uint32_t *keys, size_t cap, size_t *n);
+int b200adsb_icao_restore(b200adsb_ctx *ctx, const uint32_t *keys, size_t n);
+
+/* ------------------------------------------------------- crc.rs / mode_s/mod.rs */
+/* modes_checksum(&[u8], bits) (src/crc.rs:263-282) for n messages of 14 bytes
+ * each (host), bits = 56 or 112; syndromes to out[n].  Runs the device CRC. */
+int b200adsb_modes_checksum(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n, size_t bits,
+                            uint32_t *out);
+/* score_modes_message (src/mode_s/mod.rs:34-139) applied to n 14-byte messages
+ * in order, against and updating the context filter.  lens[i] = 7/14 (0 for
+ * None), scores[i] = score. */
+int b200adsb_score_modes_messages(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n,
+                                  uint8_t *lens, int32_t *scores);
+
+/* test hook, pure host: the 840-word CRC-24 field tables used by the scan kernel
+ * followed by the 256-entry byte table (src/crc.rs:3-260); returns 840. */
+int b200adsb_debug_crc_tabs(uint32_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ADSB_H */

@@ -1,0 +1,150 @@
+"""Pins the CPU oracle (oracle/) to the reference's own golden vectors (tests/test.rs)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+# frame-complete ground truth derived in SURVEY.md section 4: (j, phase, score)
+EXPECT_JTS = {
+    "test_1641427457780": [(21915, 7, 1400), (68286, 8, 1800), (68287, 4, 1800), (71134, 7, 1000),
+                           (130601, 5, 1400)],
+    "test_1641428165033": [(14611, 6, 1400), (36743, 5, 1400), (57293, 4, 1800), (87566, 4, 1800),
+                           (127558, 8, 1600)],
+    "test_1641428106243": [(9323, 7, 1800), (27656, 7, 1000), (33684, 5, 1400), (34915, 8, 1400),
+                           (34916, 4, 1800), (107495, 5, 1800)],
+}
+
+
+@pytest.mark.parametrize("name", sorted(EXPECT_JTS))
+def test_reference_golden_vectors(name, captures, golden_frames, oracle_mod):
+    """tests/test.rs:7-17: flush, to_mag, demodulate2400, zip with the expected bytes."""
+    o = oracle_mod.Oracle()
+    frames = o.demod_iq(captures[name], flush=True)
+    gold = [bytes.fromhex(g["hex"]) for g in golden_frames[name]]
+    # the reference zips (tests/test.rs:14): every produced frame must equal its vector
+    for f, g in zip(frames, gold):
+        assert f["msg"] == g
+    # stricter than the reference: frame count and (j, phase, score)
+    assert [(f["j"], f["phase"], f["score"]) for f in frames] == EXPECT_JTS[name]
+    # tests/test.rs:41 is a stale pre-v0.8.0 vector (CHANGELOG.md:15): unreachable by zip
+    live = len(EXPECT_JTS[name])
+    assert len(gold) - live in (0, 1)
+    assert [f["msg"] for f in frames] == gold[:live]
+
+
+def test_crc_table_matches_reference_source(oracle_mod):
+    """src/crc.rs:3-260 when the reference tree is mounted (build container only)."""
+    path = "/root/reference/src/crc.rs"
+    t = oracle_mod.crc_table()
+    assert t[0] == 0 and t[1] == 0x00FFF409 and t[2] == 0x00001C1B and t[255] == 0x00FA0480
+    if not os.path.exists(path):
+        pytest.skip("reference tree not mounted")
+    src = open(path).read()
+    body = src[src.index("CRC_TABLE"):src.index("];")]
+    vals = [int(v.replace("_", ""), 16) for v in re.findall(r"0x([0-9a-fA-F_]+)", body)]
+    assert len(vals) == 256
+    assert vals == [int(x) for x in t]
+
+
+def test_checksum_of_golden_frames(golden_frames, oracle_mod):
+    """DF17 vectors have syndrome 0; DF11 5d... has syndrome 0 (IID 0)."""
+    for name, lst in golden_frames.items():
+        for g in lst:
+            m = bytes.fromhex(g["hex"])
+            if len(m) != (14 if m[0] & 0x80 else 7):
+                continue   # tests/test.rs:41, the stale long form of a DF11
+            syn = oracle_mod.modes_checksum(m, 8 * len(m))
+            if m[0] >> 3 in (17, 11):
+                assert syn == 0, g
+
+
+def test_to_mag_layout_and_rounding(oracle_mod):
+    o = oracle_mod.Oracle()
+    iq = np.array([[0, 0], [32767, 0], [0, -32768], [-32768, -32768], [3, 4], [-358, 153]], dtype=np.int16)
+    mb = o.to_mag(iq)
+    d = oracle_mod.mag_array(mb)
+    assert mb.length == 6 and not d[:326].any() and not d[326 + 6:].any()
+    assert d[326] == 0
+    assert d[326 + 1] == 65533            # 32767/32768*65535 + .5 truncated
+    assert d[326 + 2] == 65535 and d[326 + 3] == 65535   # saturating `as u16`
+    assert d[326 + 4] == int(np.float32(np.sqrt(np.float32(25.0 / 2**30))) * np.float32(65535) + np.float32(0.5))
+    with pytest.raises(IndexError):
+        o.to_mag(np.zeros((131073, 2), dtype=np.int16))
+
+
+def test_filter_semantics(oracle_mod):
+    """icao_filter.rs: test(0) is true on an empty filter; ADSB_NT keys never match."""
+    o = oracle_mod.Oracle()
+    assert o.icao_filter_test(0)
+    assert not o.icao_filter_test(0xABCDEF)
+    o.icao_filter_add(0xABCDEF)
+    assert o.icao_filter_test(0xABCDEF)
+    o.icao_filter_add(0x123456 | oracle_mod.ADSB_NT)
+    assert not o.icao_filter_test(0x123456)
+    o.icao_flush()
+    assert not o.icao_filter_test(0xABCDEF)
+    assert oracle_mod.icao_hash(0) == 0
+
+
+def resolve_records(records_per_buffer, preloaded=frozenset(), capacity=4096, ordinals=None):
+    """Order-free evaluation of the ICAO filter used by the CUDA path,
+    restated in Python for the tests: returns per buffer [(j, phase, score, len)], and
+    the final member set."""
+    K_NONE, K_PS, K_11Z, K_11I, K_17, K_18, K_PL = range(7)
+    first = {}
+    for b, recs in enumerate(records_per_buffer):
+        ob = b if ordinals is None else ordinals[b]
+        for j, w in recs:
+            for t, wd in enumerate(w):
+                kind, key = wd >> 29, wd & 0xFFFFFF
+                if kind in (K_11Z, K_17, K_18):
+                    k = key | ((1 << 25) if kind == K_18 else 0)
+                    if k == 0:
+                        continue
+                    o = (ob, j, t)
+                    if k not in first or o < first[k]:
+                        first[k] = o
+    new = sorted((o, k) for k, o in first.items() if k not in preloaded)
+    room = capacity - len(preloaded)
+    admitted = {k: o for o, k in new[:max(room, 0)]}
+    out = []
+    for b, recs in enumerate(records_per_buffer):
+        ob = b if ordinals is None else ordinals[b]
+        res = []
+        for j, w in recs:
+            best, bt, bl = -2, 0, 7
+            for t, wd in enumerate(w):
+                kind, key = wd >> 29, wd & 0xFFFFFF
+                if kind == K_NONE:
+                    continue
+                m = key == 0 or key in preloaded or (key in admitted and admitted[key] < (ob, j, t))
+                score, ln = {K_PS: (1000 if m else -1, 7), K_11Z: (1600 if m else 750, 7),
+                             K_11I: (1000 if m else -1, 7), K_17: (1800 if m else 1400, 14),
+                             K_18: (1800 if m else 1400, 14), K_PL: (1000 if m else -2, 14)}[kind]
+                if score > best:
+                    best, bt, bl = score, t, ln
+            if best >= 0:
+                res.append((j, 4 + bt, best, bl))
+        out.append(res)
+    return out, set(preloaded) | set(admitted)
+
+
+def test_two_pass_equals_sequential(captures, oracle_mod):
+    """The order-free form reproduces the sequential filter on the captures, both flushed
+    per capture and as one 3-buffer stream with a persistent filter."""
+    names = sorted(captures)
+    o = oracle_mod.Oracle()
+    recs = [o.records(o.to_mag(captures[n])) for n in names]
+    # per capture, flushed
+    for n, r in zip(names, recs):
+        seq = oracle_mod.Oracle().demod_iq(captures[n], flush=True)
+        got, _ = resolve_records([r])
+        assert got[0] == [(f["j"], f["phase"], f["score"], len(f["msg"])) for f in seq]
+    # one stream
+    os_ = oracle_mod.Oracle()
+    seq = [os_.demod_iq(captures[n]) for n in names]
+    got, members = resolve_records(recs)
+    for g, s in zip(got, seq):
+        assert g == [(f["j"], f["phase"], f["score"], len(f["msg"])) for f in s]
+    assert members == os_.members()
