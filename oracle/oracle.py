@@ -49,7 +49,8 @@ class Record(C.Structure):
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "dump1090_oracle.c")
     hdr = os.path.join(_HERE, "dump1090_oracle.h")
-    stale = (not os.path.exists(_SO)) or any(
+    exe = os.path.join(_HERE, "orc_bench")
+    stale = (not os.path.exists(_SO)) or (not os.path.exists(exe)) or any(
         os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr)
     )
     if force or stale:
@@ -194,9 +195,19 @@ def icao_hash(a: int) -> int:
 
 
 def bench(iq: np.ndarray, n_buffers: int, spb: int, iters: int, threads: int, flush_each: bool):
+    """Times the reference routine in a separate process (oracle/orc_bench): host threads
+    inside a Python process that has numpy/torch loaded do not run in parallel in this
+    image, a plain C process does.  Returns (seconds, frames)."""
+    import json
+    import tempfile
     a = np.ascontiguousarray(iq, dtype=np.int16).reshape(-1)
     assert a.size == 2 * n_buffers * spb
-    fr = C.c_uint64(0)
-    sec = lib().orc_bench(a.ctypes.data_as(C.c_void_p), n_buffers, spb, iters, threads,
-                          int(flush_each), C.byref(fr))
-    return float(sec), int(fr.value)
+    build()
+    exe = os.path.join(_HERE, "orc_bench")
+    with tempfile.NamedTemporaryFile(suffix=".iq", dir=os.environ.get("TMPDIR", "/tmp")) as f:
+        a.tofile(f)
+        f.flush()
+        out = subprocess.run([exe, f.name, str(n_buffers), str(spb), str(iters), str(threads),
+                              str(int(flush_each))], check=True, capture_output=True, text=True).stdout
+    r = json.loads(out.strip().splitlines()[-1])
+    return float(r["sec"]), int(r["frames"])
