@@ -401,7 +401,7 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     prof_begin(c, c->other_events);
     events_finalize_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
                                                       c->d_ev_tmp, c->d_new_keys, c->d_counters,
-                                                      c->d_members);
+                                                      c->d_members, kEvSlots - 1);
     CK(c, cudaGetLastError());
     if (q.n_tiles) {
         ResolveParams rp{};

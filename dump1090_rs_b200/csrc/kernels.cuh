@@ -237,8 +237,8 @@ __device__ inline void event_add(uint32_t *ev_keys, unsigned long long *ev_ord, 
                                  uint32_t mask, uint32_t *counters, uint32_t key,
                                  unsigned long long ord)
 {
-    if ((key & 0xffffffu) == 0 && !(key & B200ADSB_ICAO_FILTER_ADSB_NT))
-        return;   // icao_filter_add(0) stores nothing (icao_filter.rs:58-60)
+    if ((key & 0xffffffu) == 0)
+        return;   // address 0 always tests true (icao_filter.rs:71,78): neither DF17/11 nor DF18 add it
     uint32_t h = hash32(key) & mask;
     for (uint32_t probe = 0; probe <= mask; probe++) {
         const uint32_t prev = atomicCAS(&ev_keys[h], 0u, key);
@@ -638,13 +638,24 @@ __global__ void events_import_kernel(const unsigned long long *pairs, uint32_t n
 // first 4096 distinct keys by first-add order; later ones are dropped.  One block.
 __global__ void __launch_bounds__(1024) events_finalize_kernel(
     const uint32_t *ev_keys, unsigned long long *ev_ord, const uint32_t *ev_used, uint32_t *ev_tmp,
-    uint32_t *new_keys, uint32_t *counters, const uint32_t *members)
+    uint32_t *new_keys, uint32_t *counters, const uint32_t *members, uint32_t ev_mask)
 {
     const uint32_t n = counters[C_EV_USED];
     const uint32_t have = counters[C_MEMBERS];
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t h = ev_used[i];
-        ev_tmp[i] = members_has(members, ev_keys[h]) ? 0u : 1u;
+        const uint32_t key = ev_keys[h];
+        bool is_new = !members_has(members, key);
+        if (is_new && (key & B200ADSB_ICAO_FILTER_ADSB_NT)) {
+            // DF18 adds addr|ADSB_NT only when icao_filter_test(addr) was false at that
+            // moment (mode_s/mod.rs:97-104): not if the plain address was in the filter
+            // before the batch or was first added earlier in it.  (If that earlier add was
+            // dropped because the table was full, this add is dropped for the same reason.)
+            const uint32_t plain = key & 0xffffffu;
+            if (members_has(members, plain) || event_first(ev_keys, ev_ord, ev_mask, plain) < ev_ord[h])
+                is_new = false;
+        }
+        ev_tmp[i] = is_new ? 1u : 0u;
     }
     __syncthreads();
     uint32_t my_new = 0;

@@ -105,6 +105,11 @@ def resolve_records(records_per_buffer, preloaded=frozenset(), capacity=4096, or
                     o = (ob, j, t)
                     if k not in first or o < first[k]:
                         first[k] = o
+    # DF18 adds addr|ADSB_NT only while icao_filter_test(addr) is still false
+    for k in [k for k in first if k >> 25]:
+        plain = k & 0xFFFFFF
+        if plain in preloaded or (plain in first and first[plain] < first[k]):
+            del first[k]
     new = sorted((o, k) for k, o in first.items() if k not in preloaded)
     room = capacity - len(preloaded)
     admitted = {k: o for o, k in new[:max(room, 0)]}
