@@ -195,10 +195,15 @@ int pick_tile(const b200adsb_ctx *c, size_t n_buffers, size_t spb)
 {
     if (c->tile_opt)
         return c->tile_opt;
-    const size_t total = n_buffers * spb;
-    size_t t = total / 592;          // aim at >= 4 tiles per SM
-    t = t / 32 * 32;
-    return (int)std::min<size_t>(std::max<size_t>(t, 512), kMaxTile);
+    // tile sizes whose halo-extended length is a whole number of 384-sample blocks;
+    // the largest that still gives every SM a few tiles
+    static const int kTiles[] = {kDefaultTile, 3544, 2008, 856, 472};
+    for (int t : kTiles) {
+        const size_t tiles = n_buffers * ((spb + t - 1) / t);
+        if (tiles >= 592)
+            return t;
+    }
+    return 472;
 }
 
 void prof_begin(b200adsb_ctx *c, std::vector<EventPair> &v)
@@ -279,9 +284,11 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     prof_begin(c, c->scan_events);
     if (q.from_mag) {
         CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+        CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         scan_kernel<true><<<grid, kThreads, L.bytes, c->stream>>>(p);
     } else {
         CK(c, cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
+        CK(c, cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         scan_kernel<false><<<grid, kThreads, L.bytes, c->stream>>>(p);
     }
     prof_end(c, c->scan_events);
@@ -593,7 +600,7 @@ int b200adsb_ctx_set_option(b200adsb_ctx *c, int option, int64_t value)
         return B200ADSB_ERR_BAD_ARG;
     switch (option) {
     case B200ADSB_OPT_TILE:
-        if (value != 0 && (value < 32 || value > kMaxTile || value % 32))
+        if (value != 0 && (value < 8 || value > kMaxTile || value % 8))
             return B200ADSB_ERR_BAD_ARG;
         c->tile_opt = (int)value;
         return B200ADSB_OK;
@@ -1072,6 +1079,30 @@ int b200adsb_score_modes_messages(b200adsb_ctx *c, const uint8_t *msgs, size_t n
             any |= m[k] != 0;
         lens[i] = !any ? 0 : ((m[0] & 0x80) ? 14 : 7);
     }
+    return B200ADSB_OK;
+}
+
+/* test hook: compares the scan kernel's fast magnitude with the IEEE-intrinsic form of
+ * utils.rs:47-55 on all 2^32 (re, im) inputs, on the GPU. */
+int b200adsb_debug_mag_sweep(b200adsb_ctx *c, uint64_t *mismatches, uint32_t *first_bad)
+{
+    if (!c || !mismatches || !first_bad)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = ensure_stage(c, 64);
+    if (rc) return rc;
+    unsigned long long *d_m = reinterpret_cast<unsigned long long *>(c->d_stage);
+    uint32_t *d_f = reinterpret_cast<uint32_t *>(d_m + 1);
+    CK(c, cudaMemsetAsync(d_m, 0, 8, c->stream));
+    CK(c, cudaMemsetAsync(d_f, 0xff, 4, c->stream));
+    mag_sweep_kernel<<<(1u << 24) / 256, 256, 0, c->stream>>>(d_m, d_f);
+    CK(c, cudaGetLastError());
+    unsigned long long m = 0;
+    CK(c, cudaMemcpyAsync(&m, d_m, 8, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(first_bad, d_f, 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *mismatches = m;
     return B200ADSB_OK;
 }
 

@@ -39,7 +39,12 @@ constexpr int kHaloTot = 296;    // mags needed per tile = T + 296 (max tap j+28
 constexpr int kStep = 384;       // 12 residues x 32 lanes: samples per warp step
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kMaxTile = 8192;
+constexpr int kChunk = 256;      // samples per warp iteration of P1 (8 per lane)
+constexpr int kDDBlock = 396;    // 384 first differences + 12 mirrored from the next block
+constexpr int kQueueCap = 2048;  // template matches awaiting the scalar gates (overflow: in place)
+constexpr int kCandCap = 1024;   // survivors decoded per window
+constexpr int kMaxTile = 8184;   // tile mag indices (< T+2) fit 13 bits; surv words <= 256
+constexpr int kDefaultTile = 7768;   // 21 blocks of 384: 252 (block, residue) items per 256 threads
 constexpr int kTabWords = 256 + 256 + 64 + 256 + 8;   // CRC-24 field tables (see build_crc_tabs)
 constexpr int kTab56 = 576;
 
@@ -82,24 +87,29 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 
 // shared memory plan of the scan kernel for tile size T
 struct ScanSmem {
-    int MP, W, WP, nw;
-    size_t off_planes, off_surv, off_tabs, off_cand, bytes;
+    int steps, MP, MPc, WP, nw;
+    size_t off_dd, off_planes, off_surv, off_tabs, off_queue, off_cand, bytes;
     __host__ __device__ explicit ScanSmem(int T)
     {
-        MP = round_up(T + kHaloTot, kStep);
-        W = MP / kStep;
-        WP = W + 1;
+        steps = (T + kHaloTot + kStep - 1) / kStep;   // 384-sample blocks (12 residues x 32)
+        MP = steps * kStep;
+        MPc = round_up(MP + 8, kChunk);               // P1 works in 256-sample warp chunks
+        WP = steps + 1;
         nw = (T + 31) / 32;
-        size_t o = (size_t)(MP + 16) * 2;
+        size_t o = (size_t)(MPc + 8) * 2;             // u16 magnitudes
         o = (o + 15) & ~(size_t)15;
+        off_dd = o;                                   // i32 first differences, 396 per block
+        o += (size_t)(kDDBlock * ((MPc + kStep - 1) / kStep + 1)) * 4;
         off_planes = o;
         o += (size_t)7 * 12 * WP * 4;
         off_surv = o;
         o += (size_t)nw * 4;
         off_tabs = o;
         o += (size_t)kTabWords * 4;
+        off_queue = o;
+        o += (size_t)kQueueCap * 2;
         off_cand = o;
-        o += (size_t)T * 2;
+        o += (size_t)kCandCap * 2;
         bytes = (o + 15) & ~(size_t)15;
     }
 };
@@ -107,6 +117,8 @@ struct ScanSmem {
 // ------------------------------------------------------------------ magnitude
 // src/utils.rs:47-55: fi = im/2^15, fq = re/2^15 (exact), fma(fi,fi, rn(fq*fq)),
 // IEEE sqrt, fma(mag, 65535, 0.5), saturating truncation (Rust `as u16`).
+// Reference form (IEEE intrinsics), used by to_mag_kernel/emit and as the in-library
+// check of the fast form below (b200adsb_debug_mag_sweep compares all 2^32 inputs).
 __device__ __forceinline__ uint32_t mag_u16(int re, int im)
 {
     const float fi = __fmul_rn(__int2float_rn(im), 0x1p-15f);
@@ -120,6 +132,34 @@ __device__ __forceinline__ uint32_t mag_u16(int re, int im)
 __device__ __forceinline__ uint32_t mag_pair(uint32_t w)  // w = re | im<<16
 {
     return mag_u16((int)(short)(w & 0xffffu), (int)(short)(w >> 16));
+}
+
+// Fast form, bit-identical on every (re, im) in int16^2 (exhaustively checked on the GPU):
+//  * int16 -> f32 without I2F: bytes of (v ^ 0x8000) under exponent 0x4B give 2^23 + v + 32768,
+//    and fma(f, 2^-15, -257) = v / 2^15 exactly;
+//  * sqrt: MUFU.RSQ seed + one FMA-based correction step, correctly rounded on the reachable
+//    set {0} U [2^-30, 2] (no denormals, no overflow);
+//  * saturating truncation: min(v, 65535) then add 2^23 rounding toward zero, so the result's
+//    low mantissa bits ARE the integer.
+// Returns the f32 bit pattern 0x4B000000 + magnitude (differences of these are differences of
+// magnitudes; the low 16 bits are the u16).
+__device__ __forceinline__ uint32_t mag_bits_fast(uint32_t w)
+{
+    const uint32_t t = w ^ 0x80008000u;
+    const float fre = __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7610));
+    const float fim = __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7632));
+    const float fq = __fmaf_rn(fre, 0x1p-15f, -257.0f);
+    const float fi = __fmaf_rn(fim, 0x1p-15f, -257.0f);
+    const float q2 = __fmul_rn(fq, fq);
+    const float x = __fmaf_rn(fi, fi, q2);
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(x, 1e-36f)));
+    const float s0 = __fmul_rn(x, y);
+    const float h = __fmul_rn(y, 0.5f);
+    const float e = __fmaf_rn(-s0, s0, x);
+    const float s = __fmaf_rn(e, h, s0);
+    const float v = fminf(__fmaf_rn(s, 65535.0f, 0.5f), 65535.0f);
+    return __float_as_uint(__fadd_rz(v, 8388608.0f));
 }
 
 // ------------------------------------------------------------------ CRC-24 by fields
@@ -293,6 +333,46 @@ __device__ __forceinline__ unsigned long long event_first(const uint32_t *ev_key
     return kNever;
 }
 
+// SNR and quiet-zone gates of one template match (demod_2400.rs:129,135-146) with the
+// template's high/signal/noise (demod_2400.rs:226-317).  e = tile mag index | case << 13.
+__device__ __forceinline__ void gate_eval(const uint16_t *mag, uint32_t *surv, uint32_t e)
+{
+    const int mi = (int)(e & 0x1fffu);
+    const uint32_t cs = e >> 13;
+    const uint16_t *pp = mag + mi;
+    int high;
+    uint32_t sig, noise;
+    if (cs == 0) {
+        high = ((int)pp[1] + pp[3] + pp[9] + pp[11] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[3] + pp[9];
+        noise = (uint32_t)pp[5] + pp[6] + pp[7];
+    } else if (cs == 1) {
+        high = ((int)pp[1] + pp[3] + pp[9] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[3] + pp[9] + pp[12];
+        noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
+    } else if (cs == 2) {
+        high = ((int)pp[1] + pp[3] + pp[4] + pp[9] + pp[10] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[12];
+        noise = (uint32_t)pp[6] + pp[7];
+    } else if (cs == 3) {
+        high = ((int)pp[1] + pp[4] + pp[10] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[4] + pp[10] + pp[12];
+        noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
+    } else {
+        high = ((int)pp[1] + pp[2] + pp[4] + pp[10] + pp[12]) / 4;
+        sig = (uint32_t)pp[4] + pp[10] + pp[12];
+        noise = (uint32_t)pp[6] + pp[7] + pp[8];
+    }
+    if (sig * 2 < 3 * noise)   // demod_2400.rs:129
+        return;
+    const int mx = max(max(max((int)pp[5], (int)pp[6]), max((int)pp[7], (int)pp[8])),
+                       max(max(max((int)pp[14], (int)pp[15]), max((int)pp[16], (int)pp[17])), (int)pp[18]));
+    if (mx >= high)            // demod_2400.rs:135-146
+        return;
+    const int jl = mi - kHaloFront;
+    atomicOr(&surv[jl >> 5], 1u << (jl & 31));
+}
+
 // ------------------------------------------------------------------ preamble templates
 // plane[rho][w] bit b  <->  tile mag index 12*(32w+b)+rho.  term(s) returns, for the 32
 // positions of item (rho, w), the plane bit of index position+s.
@@ -306,18 +386,26 @@ __device__ __forceinline__ uint32_t plane_term(const uint32_t *plane, int WP, in
 }
 
 // ================================================================== scan kernel
+// dd layout: first differences d[i] = m[i+1]-m[i] of the tile's magnitudes, 384 per block
+// padded to 396 words; the 12 pad words repeat the next block's first 12, so a lane that
+// walks one residue class (i = 12q + rho, q = 32 consecutive) reads d[i..i+2] with plain
+// strides and 32 consecutive (block, rho) items hit 32 different banks.
+__device__ __forceinline__ int dd_pos(int i) { return kDDBlock * (i / kStep) + (i % kStep); }
+
 template <bool FROM_MAG>
-__global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
+__global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const ScanSmem L(p.T);
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
+    int *dd = reinterpret_cast<int *>(smem + L.off_dd);
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [7][12][WP]
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
+    uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
     __shared__ uint32_t s_warp_tot[kWarps];
-    __shared__ uint32_t s_base, s_count, s_ok;
+    __shared__ uint32_t s_base, s_count, s_ok, s_qn;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -331,38 +419,72 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
         return;
     }
     const int npos = min(p.T, len - tile_start);
-    const int steps = (npos + kHaloTot + kStep - 1) / kStep;   // warp steps actually needed
+    const int steps = (npos + kHaloTot + kStep - 1) / kStep;   // 384-blocks actually needed
     const int MPe = steps * kStep;
     const int WP = L.WP;
 
-    // ---- P1: magnitudes of tile mag index [0, MPe+16) -> shared memory
-    if (!FROM_MAG) {
-        const int16_t *buf = reinterpret_cast<const int16_t *>(p.in) + 2ull * b * p.stride;
-        const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of mag[0]
-        for (int c = tid; c < (MPe + 16) / 4; c += kThreads) {
-            const int s = s0 + 4 * c;
-            uint32_t m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-            if (s >= 0 && s + 3 < len && p.vec_ok) {
-                const int4 v = __ldg(reinterpret_cast<const int4 *>(buf + 2ll * s));
-                m0 = mag_pair((uint32_t)v.x);
-                m1 = mag_pair((uint32_t)v.y);
-                m2 = mag_pair((uint32_t)v.z);
-                m3 = mag_pair((uint32_t)v.w);
+    // ---- P1: magnitudes m[0, MPe+8) (u16) and differences d[0, MPe+4) (i32) -> shared memory.
+    // A warp takes 256 consecutive samples per iteration, 8 per lane (two 16-byte loads).
+    {
+        const int nchunk = (MPe + 8 + kChunk - 1) / kChunk;
+        const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of m[0]
+        const int i0 = tile_start - kHaloFront;                  // data index of m[0]
+        for (int ch = warp; ch < nchunk; ch += kWarps) {
+            const int mi = ch * kChunk + 8 * lane;
+            uint32_t r[9];   // 0x4B000000 + magnitude
+            if (!FROM_MAG) {
+                const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
+                const int s = s0 + mi;
+                if (s >= 0 && s + 7 < len && p.vec_ok) {
+                    const int4 v0 = __ldg(reinterpret_cast<const int4 *>(b32 + s));
+                    const int4 v1 = __ldg(reinterpret_cast<const int4 *>(b32 + s + 4));
+                    r[0] = mag_bits_fast((uint32_t)v0.x);
+                    r[1] = mag_bits_fast((uint32_t)v0.y);
+                    r[2] = mag_bits_fast((uint32_t)v0.z);
+                    r[3] = mag_bits_fast((uint32_t)v0.w);
+                    r[4] = mag_bits_fast((uint32_t)v1.x);
+                    r[5] = mag_bits_fast((uint32_t)v1.y);
+                    r[6] = mag_bits_fast((uint32_t)v1.z);
+                    r[7] = mag_bits_fast((uint32_t)v1.w);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int se = s + e;
+                        r[e] = (se >= 0 && se < len) ? mag_bits_fast(__ldg(b32 + se)) : 0x4B000000u;
+                    }
+                }
+                r[8] = __shfl_down_sync(0xffffffffu, r[0], 1);
+                if (lane == 31) {
+                    const int se = s + 8;
+                    r[8] = (se >= 0 && se < len) ? mag_bits_fast(__ldg(b32 + se)) : 0x4B000000u;
+                }
             } else {
-                const uint32_t *b32 = reinterpret_cast<const uint32_t *>(buf);
-                if (s >= 0 && s < len) m0 = mag_pair(__ldg(b32 + s));
-                if (s + 1 >= 0 && s + 1 < len) m1 = mag_pair(__ldg(b32 + s + 1));
-                if (s + 2 >= 0 && s + 2 < len) m2 = mag_pair(__ldg(b32 + s + 2));
-                if (s + 3 >= 0 && s + 3 < len) m3 = mag_pair(__ldg(b32 + s + 3));
+                const uint16_t *d = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
+#pragma unroll
+                for (int e = 0; e < 9; e++) {
+                    const int idx = i0 + mi + e;
+                    r[e] = 0x4B000000u + ((idx >= 0 && idx < kMagLen) ? (uint32_t)__ldg(d + idx) : 0u);
+                }
             }
-            *reinterpret_cast<uint2 *>(mag + 4 * c) = make_uint2(m0 | (m1 << 16), m2 | (m3 << 16));
-        }
-    } else {
-        const uint16_t *d = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
-        const int i0 = tile_start - kHaloFront;   // data index of mag[0]
-        for (int c = tid; c < MPe + 16; c += kThreads) {
-            const int idx = i0 + c;
-            mag[c] = (idx >= 0 && idx < kMagLen) ? __ldg(d + idx) : (uint16_t)0;
+            // u16 magnitudes, 8 per lane
+            *reinterpret_cast<uint4 *>(mag + mi) =
+                make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410),
+                           __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
+            // first differences (bit patterns share the binade, so they subtract like integers)
+            int dv[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                dv[e] = (int)(r[e + 1] - r[e]);
+            const int blk = mi / kStep, off = mi - blk * kStep;
+            int *dst = dd + kDDBlock * blk + off;
+            *reinterpret_cast<int4 *>(dst) = make_int4(dv[0], dv[1], dv[2], dv[3]);
+            *reinterpret_cast<int4 *>(dst + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
+            if (off < 12 && blk > 0) {   // mirror into the previous block's pad
+                int *pad = dd + kDDBlock * (blk - 1) + kStep + off;
+                *reinterpret_cast<int4 *>(pad) = make_int4(dv[0], dv[1], dv[2], dv[3]);
+                if (off == 0)
+                    *reinterpret_cast<int4 *>(pad + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
+            }
         }
     }
     for (int c = tid; c < L.nw; c += kThreads)
@@ -371,61 +493,56 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
         tabs[c] = __ldg(p.crc_tabs + c);
     for (int c = tid; c < 7 * 12; c += kThreads)
         planes[c * WP + steps] = 0;   // pad word read by funnel shifts
+    if (tid == 0)
+        s_qn = 0;
     __syncthreads();
 
-    // ---- P2: correlator sign planes S[phi] and edge planes R (rising), F (falling)
-    for (int step = warp; step < steps; step += kWarps) {
-        const uint16_t *mp = mag + kStep * step + 12 * lane;
-        int m[16];
+    // ---- P2: bit planes.  One lane = one residue class rho of one 384-block: 32 samples at
+    // stride 12, each contributing one bit to the five correlator-sign planes S[phi] and to
+    // the edge planes R (rising), F (falling); bits are shifted in with funnel shifts.
+    // demod_2400.rs:72-83 on negated first differences u,v,w (so that "x > 0" is a sign bit):
+    //   -[5,-3,-2] = 5u+2v   -[4,-1,-3] = 4u+3v   -[3,1,-4] = 3u+4v   -[2,3,-5] = 2u+5v
+    //   -[1,5,-5,-1] = u+6v+w
+    for (int item = tid; item < 12 * steps; item += kThreads) {
+        const int blk = item / 12, rho = item - 12 * blk;
+        const int *dp = dd + kDDBlock * blk + rho;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, ar = 0, af = 0;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const uint2 v = *reinterpret_cast<const uint2 *>(mp + 4 * q);
-            m[4 * q + 0] = (int)(v.x & 0xffffu);
-            m[4 * q + 1] = (int)(v.x >> 16);
-            m[4 * q + 2] = (int)(v.y & 0xffffu);
-            m[4 * q + 3] = (int)(v.y >> 16);
-        }
-#pragma unroll
-        for (int rho = 0; rho < 12; rho++) {
-            // demod_2400.rs:72-83 written on first differences u,v,w:
-            //   [5,-3,-2]->5u+2v  [4,-1,-3]->4u+3v  [3,1,-4]->3u+4v  [2,3,-5]->2u+5v
-            //   [1,5,-5,-1]->u+6v+w
-            const int u = m[rho] - m[rho + 1], v = m[rho + 1] - m[rho + 2],
-                      w = m[rho + 2] - m[rho + 3];
+        for (int q = 31; q >= 0; q--) {
+            const int u = dp[12 * q], v = dp[12 * q + 1], w = dp[12 * q + 2];
             const int g = v - u;
             const int x0 = 5 * u + 2 * v, x1 = x0 + g, x2 = x1 + g, x3 = x2 + g, x4 = x3 + g + w;
-            const uint32_t b0 = __ballot_sync(0xffffffffu, x0 > 0);
-            const uint32_t b1 = __ballot_sync(0xffffffffu, x1 > 0);
-            const uint32_t b2 = __ballot_sync(0xffffffffu, x2 > 0);
-            const uint32_t b3 = __ballot_sync(0xffffffffu, x3 > 0);
-            const uint32_t b4 = __ballot_sync(0xffffffffu, x4 > 0);
-            const uint32_t br = __ballot_sync(0xffffffffu, u < 0);
-            const uint32_t bf = __ballot_sync(0xffffffffu, u > 0);
-            if (lane == 0) {
-                planes[(0 * 12 + rho) * WP + step] = b0;
-                planes[(1 * 12 + rho) * WP + step] = b1;
-                planes[(2 * 12 + rho) * WP + step] = b2;
-                planes[(3 * 12 + rho) * WP + step] = b3;
-                planes[(4 * 12 + rho) * WP + step] = b4;
-                planes[(5 * 12 + rho) * WP + step] = br;
-                planes[(6 * 12 + rho) * WP + step] = bf;
-            }
+            a0 = __funnelshift_l((uint32_t)x0, a0, 1);
+            a1 = __funnelshift_l((uint32_t)x1, a1, 1);
+            a2 = __funnelshift_l((uint32_t)x2, a2, 1);
+            a3 = __funnelshift_l((uint32_t)x3, a3, 1);
+            a4 = __funnelshift_l((uint32_t)x4, a4, 1);
+            af = __funnelshift_l((uint32_t)u, af, 1);      // m[i+1]-m[i] < 0: falling
+            ar = __funnelshift_l((uint32_t)(-u), ar, 1);   // rising
         }
+        uint32_t *pl = planes + rho * WP + blk;
+        pl[0 * 12 * WP] = a0;
+        pl[1 * 12 * WP] = a1;
+        pl[2 * 12 * WP] = a2;
+        pl[3 * 12 * WP] = a3;
+        pl[4 * 12 * WP] = a4;
+        pl[5 * 12 * WP] = ar;
+        pl[6 * 12 * WP] = af;
     }
     __syncthreads();
 
-    // ---- P3: preamble templates, 32 positions per item, then the scalar gates
+    // ---- P3a: preamble templates, 32 positions per item; matches go to a queue
     {
         const uint32_t *R = planes + 5 * 12 * WP, *F = planes + 6 * 12 * WP;
         for (int item = tid; item < 12 * steps; item += kThreads) {
-            const int rho = item / steps, w = item - rho * steps;
+            const int w = item / 12, rho = item - 12 * w;
             // valid positions: 2 <= mi < npos+2 with mi = 12*(32w+bit)+rho
             const int q_lo = (rho < kHaloFront) ? 1 : 0;
             const int q_hi = (npos + kHaloFront - rho + 11) / 12;   // exclusive
-            int lo = max(q_lo - 32 * w, 0), hi = min(q_hi - 32 * w, 32);
+            const int lo = max(q_lo - 32 * w, 0), hi = min(q_hi - 32 * w, 32);
             if (hi <= lo)
                 continue;
-            uint32_t valid = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
+            const uint32_t valid = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
             const uint32_t quick = plane_term(R, WP, rho, w, 0) & plane_term(F, WP, rho, w, 12) & valid;
             if (!quick)
                 continue;
@@ -442,52 +559,38 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
             const uint32_t T6 = F1 & R3 & F4 & R9 & F10 & R11;
             const uint32_t T7 = F2 & R3 & F4 & R9 & F10 & R11;
             uint32_t any = quick & (T3 | T4 | T5 | T6 | T7);
+            if (!any)
+                continue;
+            const uint32_t c0 = T3, c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5);
+            uint32_t qi = atomicAdd(&s_qn, (uint32_t)__popc(any));
             while (any) {
                 const int bit = __ffs(any) - 1;
                 any &= any - 1;
-                const int mi = 12 * (32 * w + bit) + rho;
-                const uint16_t *pp = mag + mi;
-                int high;
-                uint32_t sig, noise;
-                if ((T3 >> bit) & 1u) {
-                    high = ((int)pp[1] + pp[3] + pp[9] + pp[11] + pp[12]) / 4;
-                    sig = (uint32_t)pp[1] + pp[3] + pp[9];
-                    noise = (uint32_t)pp[5] + pp[6] + pp[7];
-                } else if ((T4 >> bit) & 1u) {
-                    high = ((int)pp[1] + pp[3] + pp[9] + pp[12]) / 4;
-                    sig = (uint32_t)pp[1] + pp[3] + pp[9] + pp[12];
-                    noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
-                } else if ((T5 >> bit) & 1u) {
-                    high = ((int)pp[1] + pp[3] + pp[4] + pp[9] + pp[10] + pp[12]) / 4;
-                    sig = (uint32_t)pp[1] + pp[12];
-                    noise = (uint32_t)pp[6] + pp[7];
-                } else if ((T6 >> bit) & 1u) {
-                    high = ((int)pp[1] + pp[4] + pp[10] + pp[12]) / 4;
-                    sig = (uint32_t)pp[1] + pp[4] + pp[10] + pp[12];
-                    noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
-                } else {
-                    high = ((int)pp[1] + pp[2] + pp[4] + pp[10] + pp[12]) / 4;
-                    sig = (uint32_t)pp[4] + pp[10] + pp[12];
-                    noise = (uint32_t)pp[6] + pp[7] + pp[8];
-                }
-                if (sig * 2 < 3 * noise)   // demod_2400.rs:129
-                    continue;
-                // demod_2400.rs:135-146
-                const int mx = max(max(max((int)pp[5], (int)pp[6]), max((int)pp[7], (int)pp[8])),
-                                   max(max(max((int)pp[14], (int)pp[15]), max((int)pp[16], (int)pp[17])),
-                                       (int)pp[18]));
-                if (mx >= high)
-                    continue;
-                const int jl = mi - kHaloFront;
-                atomicOr(&surv[jl >> 5], 1u << (jl & 31));
+                const uint32_t cs = ((c0 >> bit) & 1u) ? 0u : ((c1 >> bit) & 1u) ? 1u : ((c2 >> bit) & 1u) ? 2u
+                                    : ((c3 >> bit) & 1u) ? 3u : 4u;
+                const uint32_t mi = (uint32_t)(12 * (32 * w + bit) + rho);
+                const uint32_t e = mi | (cs << 13);
+                if (qi < (uint32_t)kQueueCap)
+                    queue[qi] = (uint16_t)e;
+                else
+                    gate_eval(mag, surv, e);     // queue full: evaluate in place
+                qi++;
             }
         }
     }
     __syncthreads();
-
-    // ---- P4a: ordered list of surviving positions (ascending j)
+    // ---- P3b: SNR and quiet-zone gates, one queue entry per thread
     {
-        uint32_t wv = (tid < L.nw) ? surv[tid] : 0u;   // nw <= 256 == kThreads
+        const int qn = (int)min(s_qn, (uint32_t)kQueueCap);
+        for (int i = tid; i < qn; i += kThreads)
+            gate_eval(mag, surv, queue[i]);
+    }
+    __syncthreads();
+
+    // ---- P4a: count survivors, reserve pool space (positions are emitted in ascending j)
+    uint32_t wv = (tid < L.nw) ? surv[tid] : 0u;   // nw <= 256 == kThreads
+    int my_off;
+    {
         const int cnt = __popc(wv);
         int incl = cnt;
 #pragma unroll
@@ -499,19 +602,14 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
         if (lane == 31)
             s_warp_tot[warp] = (uint32_t)incl;
         __syncthreads();
-        int off = incl - cnt;
+        my_off = incl - cnt;
         uint32_t total = 0;
 #pragma unroll
         for (int wi = 0; wi < kWarps; wi++) {
             const uint32_t t = s_warp_tot[wi];
             if (wi < warp)
-                off += (int)t;
+                my_off += (int)t;
             total += t;
-        }
-        while (wv) {
-            const int bit = __ffs(wv) - 1;
-            wv &= wv - 1;
-            cand[off++] = (uint16_t)(tid * 32 + bit);
         }
         if (tid == 0) {
             uint32_t base = 0, ok = 1;
@@ -533,11 +631,25 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
     if (!s_ok || s_count == 0)
         return;
 
-    // ---- P4b: five try-phases per survivor -> record words + ICAO add-events
-    {
-        const int C = (int)s_count;
-        const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
-        for (int item = tid; item < 5 * C; item += kThreads) {
+    // ---- P4b: five try-phases per survivor -> record words + ICAO add-events,
+    // in windows of kCandCap survivors
+    const int C = (int)s_count;
+    const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
+    for (int win = 0; win < C; win += kCandCap) {
+        {
+            uint32_t wv2 = wv;
+            int off = my_off;
+            while (wv2) {
+                const int bit = __ffs(wv2) - 1;
+                wv2 &= wv2 - 1;
+                if (off >= win && off < win + kCandCap)
+                    cand[off - win] = (uint16_t)(tid * 32 + bit);
+                off++;
+            }
+        }
+        __syncthreads();
+        const int Cw = min(kCandCap, C - win);
+        for (int item = tid; item < 5 * Cw; item += kThreads) {
             const int c = item / 5, tt = item - 5 * c;
             const int jl = cand[c];
             const int P0 = 5 * (jl + kHaloFront + 19) + 4 + tt;   // demod_2400.rs:158-160
@@ -553,7 +665,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
             const uint32_t wd = classify_fields(tabs, f);
             const uint32_t kind = wd >> 29;
             const uint32_t j = (uint32_t)(tile_start + jl);
-            uint32_t *rec = p.rec + 6ull * (s_base + (uint32_t)c);
+            uint32_t *rec = p.rec + 6ull * (s_base + (uint32_t)(win + c));
             rec[1 + tt] = wd;
             if (tt == 0)
                 rec[0] = j;
@@ -563,6 +675,7 @@ __global__ void __launch_bounds__(kThreads) scan_kernel(const ScanParams p)
                           ord_buf | ((unsigned long long)j << 3) | (unsigned long long)tt);
             }
         }
+        __syncthreads();
     }
 }
 
@@ -575,6 +688,23 @@ __global__ void to_mag_kernel(const uint32_t *__restrict__ iq, int n, uint16_t *
         return;
     const int s = i - kTrailing;
     data[i] = (s >= 0 && s < n) ? (uint16_t)mag_pair(__ldg(iq + s)) : (uint16_t)0;
+}
+
+// exhaustive check of mag_bits_fast against the IEEE form over all 2^32 (re, im) inputs
+__global__ void mag_sweep_kernel(unsigned long long *mismatches, uint32_t *first_bad)
+{
+    const uint32_t hi = blockIdx.x * blockDim.x + threadIdx.x;   // 2^24 threads x 256 inputs
+    uint32_t bad = 0;
+    for (uint32_t lo = 0; lo < 256; lo++) {
+        const uint32_t w = (hi << 8) | lo;
+        const uint32_t fast = mag_bits_fast(w);
+        if ((fast & 0xffffu) != mag_pair(w) || (fast >> 16) != 0x4B00u) {
+            bad++;
+            atomicMin(first_bad, w);
+        }
+    }
+    if (bad)
+        atomicAdd(mismatches, (unsigned long long)bad);
 }
 
 // ================================================================== message-level kernels

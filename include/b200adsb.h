@@ -51,7 +51,7 @@ enum {
 
 /* context options (b200adsb_ctx_set_option) */
 enum {
-    B200ADSB_OPT_TILE = 1,        /* output positions per thread block tile (multiple of 32) */
+    B200ADSB_OPT_TILE = 1,        /* output positions per thread block tile (multiple of 8, <= 8184) */
     B200ADSB_OPT_POOL_SHIFT = 2,  /* candidate pool = positions >> shift (grown on demand)    */
     B200ADSB_OPT_PROFILE = 3,     /* 1: bracket kernels with CUDA events (b200adsb_timing)    */
     B200ADSB_OPT_H2D_CHUNK = 4    /* buffers per host->device pipeline chunk (host batch API) */
@@ -177,6 +177,10 @@ int b200adsb_modes_checksum(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n, 
  * None), scores[i] = score. */
 int b200adsb_score_modes_messages(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n,
                                   uint8_t *lens, int32_t *scores);
+
+/* test hook: exhaustive GPU comparison of the scan kernel's fast magnitude arithmetic
+ * with the IEEE-intrinsic statement of src/utils.rs:47-55 over all 2^32 inputs. */
+int b200adsb_debug_mag_sweep(b200adsb_ctx *ctx, uint64_t *mismatches, uint32_t *first_bad);
 
 /* test hook, pure host: the 840-word CRC-24 field tables used by the scan kernel
  * followed by the 256-entry byte table (src/crc.rs:3-260); returns 840. */

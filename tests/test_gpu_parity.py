@@ -80,7 +80,7 @@ def test_stream_of_captures_persistent_filter(ctx, captures, oracle_mod):
     assert list(counts) == [sum(1 for f in ref if f["buffer"] == b) for b in range(3)]
 
 
-@pytest.mark.parametrize("tile", [32, 352, 512, 1024, 4096, 8192])
+@pytest.mark.parametrize("tile", [8, 32, 88, 352, 472, 1024, 4096, 7768, 8184])
 def test_tile_sizes(tile, pkg, captures, oracle_mod):
     from dump1090_rs_b200 import _ffi
     c = pkg.Context(0)
@@ -103,6 +103,18 @@ def test_to_mag_random_full_range(ctx, oracle_mod):
     d2, n2 = ctx.to_mag(iq2)
     assert n2 == 65536
     assert np.array_equal(d2, oracle_mod.mag_array(oracle_mod.Oracle().to_mag(iq2)))
+
+
+def test_fast_magnitude_exhaustive(ctx):
+    """The scan kernel's magnitude (no I2F/F2I, rsqrt-seeded sqrt) equals the IEEE statement of
+    utils.rs:47-55 on every one of the 2^32 (re, im) inputs; the latter is checked against the
+    oracle by test_to_mag_random_full_range (to_mag_kernel uses it)."""
+    import ctypes as C
+    from dump1090_rs_b200 import _ffi
+    m, f = C.c_uint64(123), C.c_uint32(0)
+    rc = _ffi.lib().b200adsb_debug_mag_sweep(ctx._h, C.byref(m), C.byref(f))
+    assert rc == 0
+    assert m.value == 0, f"{m.value} mismatches, first at re|im<<16 = {f.value:#010x}"
 
 
 # ---------------------------------------------------------------- synthetic streams
