@@ -39,10 +39,11 @@ constexpr int kHaloTot = 296;    // mags needed per tile = T + 296 (max tap j+28
 constexpr int kStep = 384;       // 12 residues x 32 lanes: samples per warp step
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 256;      // samples per warp iteration of P1 (8 per lane)
+constexpr int kChunk = 248;      // new samples per warp iteration of P1 (8 per lane, lane 31 overlaps)
 constexpr int kDDBlock = 396;    // 384 first differences + 12 mirrored from the next block
-constexpr int kQueueCap = 2048;  // template matches awaiting the scalar gates (overflow: in place)
-constexpr int kCandCap = 1024;   // survivors decoded per window
+constexpr int kQueueCap = 512;   // template matches per template case awaiting the gates (overflow: in place)
+constexpr int kCandCap = 352;    // survivors decoded per window
+constexpr int kFieldItems = 5 * kCandCap;   // (survivor, try_phase) items whose fields are staged
 constexpr int kMaxTile = 8184;   // tile mag indices (< T+2) fit 13 bits; surv words <= 256
 constexpr int kDefaultTile = 7768;   // 21 blocks of 384: 252 (block, residue) items per 256 threads
 constexpr int kTabWords = 256 + 256 + 64 + 256 + 8;   // CRC-24 field tables (see build_crc_tabs)
@@ -87,19 +88,22 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 
 // shared memory plan of the scan kernel for tile size T
 struct ScanSmem {
-    int steps, MP, MPc, WP, nw;
+    int steps, MP, MPc, WP, nw, dd_words;
     size_t off_dd, off_planes, off_surv, off_tabs, off_queue, off_cand, bytes;
     __host__ __device__ explicit ScanSmem(int T)
     {
         steps = (T + kHaloTot + kStep - 1) / kStep;   // 384-sample blocks (12 residues x 32)
         MP = steps * kStep;
-        MPc = round_up(MP + 8, kChunk);               // P1 works in 256-sample warp chunks
+        MPc = round_up(MP + 16, kChunk) + 8;          // P1 works in 248-sample warp chunks (+ lane 31)
         WP = steps + 1;
         nw = (T + 31) / 32;
         size_t o = (size_t)(MPc + 8) * 2;             // u16 magnitudes
         o = (o + 15) & ~(size_t)15;
-        off_dd = o;                                   // i32 first differences, 396 per block
-        o += (size_t)(kDDBlock * ((MPc + kStep - 1) / kStep + 1)) * 4;
+        off_dd = o;                                   // i32 first differences, 396 per block;
+        dd_words = kDDBlock * ((MPc + kStep - 1) / kStep + 1);
+        if (dd_words < kFieldItems * 5)               // later reused as the P4 field buffer
+            dd_words = kFieldItems * 5;
+        o += (size_t)dd_words * 4;
         off_planes = o;
         o += (size_t)7 * 12 * WP * 4;
         off_surv = o;
@@ -107,7 +111,7 @@ struct ScanSmem {
         off_tabs = o;
         o += (size_t)kTabWords * 4;
         off_queue = o;
-        o += (size_t)kQueueCap * 2;
+        o += (size_t)5 * kQueueCap * 2;
         off_cand = o;
         o += (size_t)kCandCap * 2;
         bytes = (o + 15) & ~(size_t)15;
@@ -134,32 +138,87 @@ __device__ __forceinline__ uint32_t mag_pair(uint32_t w)  // w = re | im<<16
     return mag_u16((int)(short)(w & 0xffffu), (int)(short)(w >> 16));
 }
 
-// Fast form, bit-identical on every (re, im) in int16^2 (exhaustively checked on the GPU):
-//  * int16 -> f32 without I2F: bytes of (v ^ 0x8000) under exponent 0x4B give 2^23 + v + 32768,
-//    and fma(f, 2^-15, -257) = v / 2^15 exactly;
-//  * sqrt: MUFU.RSQ seed + one FMA-based correction step, correctly rounded on the reachable
-//    set {0} U [2^-30, 2] (no denormals, no overflow);
-//  * saturating truncation: min(v, 65535) then add 2^23 rounding toward zero, so the result's
-//    low mantissa bits ARE the integer.
-// Returns the f32 bit pattern 0x4B000000 + magnitude (differences of these are differences of
-// magnitudes; the low 16 bits are the u16).
+// Fast form: two samples per instruction with Blackwell's packed f32x2 pipe (FFMA2/FMUL2/
+// FADD2), bit-identical to the form above on every (re, im) in int16^2 (exhaustively
+// checked on the GPU by b200adsb_debug_mag_sweep):
+//  * int16 -> f32 without I2F: bytes of (v ^ 0x8000) under exponent 0x4B give
+//    2^23 + v + 32768, and fma(f, 2^-15, -257) = v / 2^15 exactly;
+//  * sqrt: MUFU.RSQ seed y, s0 = x*y, then s = s0 + (x - s0^2) * y/2 with the residual
+//    in FMA form, correctly rounded on the reachable set {0} U [2^-30, 2] (x + 1e-30 == x
+//    there, and keeps rsqrt finite at 0); the /2 is folded as exact power-of-two scalings;
+//  * saturating truncation: min(v, 65535) then add 2^23 rounding toward zero, so the
+//    result's low mantissa bits ARE the integer.
+// Returns the f32 bit patterns 0x4B000000 + magnitude (differences of these are
+// differences of magnitudes; the low 16 bits are the u16).
+typedef unsigned long long u64x;
+__device__ __forceinline__ u64x f2_pack(float a, float b)
+{
+    u64x r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(u64x v, float &a, float &b)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ u64x f2_fma(u64x a, u64x b, u64x c)
+{
+    u64x r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ u64x f2_mul(u64x a, u64x b)
+{
+    u64x r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64x f2_add(u64x a, u64x b)
+{
+    u64x r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64x f2_add_rz(u64x a, u64x b)
+{
+    u64x r;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ void mag_bits_fast2(uint32_t wa, uint32_t wb, uint32_t &ra, uint32_t &rb)
+{
+    const uint32_t ta = wa ^ 0x80008000u, tb = wb ^ 0x80008000u;
+    const u64x fre = f2_pack(__uint_as_float(__byte_perm(ta, 0x4B000000u, 0x7610)),
+                             __uint_as_float(__byte_perm(tb, 0x4B000000u, 0x7610)));
+    const u64x fim = f2_pack(__uint_as_float(__byte_perm(ta, 0x4B000000u, 0x7632)),
+                             __uint_as_float(__byte_perm(tb, 0x4B000000u, 0x7632)));
+    const u64x c15 = f2_pack(0x1p-15f, 0x1p-15f), m257 = f2_pack(-257.0f, -257.0f);
+    const u64x fq = f2_fma(fre, c15, m257), fi = f2_fma(fim, c15, m257);
+    const u64x x = f2_fma(fi, fi, f2_mul(fq, fq));
+    float xa, xb, ya, yb;
+    f2_unpack(f2_add(x, f2_pack(1e-30f, 1e-30f)), xa, xb);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ya) : "f"(xa));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yb) : "f"(xb));
+    const u64x y = f2_pack(ya, yb);
+    const u64x s0 = f2_mul(x, y);
+    const u64x t = f2_mul(s0, f2_pack(-0.5f, -0.5f));          // -s0/2 (exact)
+    const u64x hx = f2_mul(x, f2_pack(0.5f, 0.5f));            // x/2 (exact)
+    const u64x eh = f2_fma(t, s0, hx);                          // (x - s0^2)/2, one rounding
+    const u64x s = f2_fma(eh, y, s0);                           // s0 + (x - s0^2) * y/2
+    float va, vb;
+    f2_unpack(f2_fma(s, f2_pack(65535.0f, 65535.0f), f2_pack(0.5f, 0.5f)), va, vb);
+    const u64x r = f2_add_rz(f2_pack(fminf(va, 65535.0f), fminf(vb, 65535.0f)),
+                             f2_pack(8388608.0f, 8388608.0f));
+    float fa, fb;
+    f2_unpack(r, fa, fb);
+    ra = __float_as_uint(fa);
+    rb = __float_as_uint(fb);
+}
 __device__ __forceinline__ uint32_t mag_bits_fast(uint32_t w)
 {
-    const uint32_t t = w ^ 0x80008000u;
-    const float fre = __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7610));
-    const float fim = __uint_as_float(__byte_perm(t, 0x4B000000u, 0x7632));
-    const float fq = __fmaf_rn(fre, 0x1p-15f, -257.0f);
-    const float fi = __fmaf_rn(fim, 0x1p-15f, -257.0f);
-    const float q2 = __fmul_rn(fq, fq);
-    const float x = __fmaf_rn(fi, fi, q2);
-    float y;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(fmaxf(x, 1e-36f)));
-    const float s0 = __fmul_rn(x, y);
-    const float h = __fmul_rn(y, 0.5f);
-    const float e = __fmaf_rn(-s0, s0, x);
-    const float s = __fmaf_rn(e, h, s0);
-    const float v = fminf(__fmaf_rn(s, 65535.0f, 0.5f), 65535.0f);
-    return __float_as_uint(__fadd_rz(v, 8388608.0f));
+    uint32_t a, b;
+    mag_bits_fast2(w, w, a, b);
+    return a;
 }
 
 // ------------------------------------------------------------------ CRC-24 by fields
@@ -333,46 +392,6 @@ __device__ __forceinline__ unsigned long long event_first(const uint32_t *ev_key
     return kNever;
 }
 
-// SNR and quiet-zone gates of one template match (demod_2400.rs:129,135-146) with the
-// template's high/signal/noise (demod_2400.rs:226-317).  e = tile mag index | case << 13.
-__device__ __forceinline__ void gate_eval(const uint16_t *mag, uint32_t *surv, uint32_t e)
-{
-    const int mi = (int)(e & 0x1fffu);
-    const uint32_t cs = e >> 13;
-    const uint16_t *pp = mag + mi;
-    int high;
-    uint32_t sig, noise;
-    if (cs == 0) {
-        high = ((int)pp[1] + pp[3] + pp[9] + pp[11] + pp[12]) / 4;
-        sig = (uint32_t)pp[1] + pp[3] + pp[9];
-        noise = (uint32_t)pp[5] + pp[6] + pp[7];
-    } else if (cs == 1) {
-        high = ((int)pp[1] + pp[3] + pp[9] + pp[12]) / 4;
-        sig = (uint32_t)pp[1] + pp[3] + pp[9] + pp[12];
-        noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
-    } else if (cs == 2) {
-        high = ((int)pp[1] + pp[3] + pp[4] + pp[9] + pp[10] + pp[12]) / 4;
-        sig = (uint32_t)pp[1] + pp[12];
-        noise = (uint32_t)pp[6] + pp[7];
-    } else if (cs == 3) {
-        high = ((int)pp[1] + pp[4] + pp[10] + pp[12]) / 4;
-        sig = (uint32_t)pp[1] + pp[4] + pp[10] + pp[12];
-        noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
-    } else {
-        high = ((int)pp[1] + pp[2] + pp[4] + pp[10] + pp[12]) / 4;
-        sig = (uint32_t)pp[4] + pp[10] + pp[12];
-        noise = (uint32_t)pp[6] + pp[7] + pp[8];
-    }
-    if (sig * 2 < 3 * noise)   // demod_2400.rs:129
-        return;
-    const int mx = max(max(max((int)pp[5], (int)pp[6]), max((int)pp[7], (int)pp[8])),
-                       max(max(max((int)pp[14], (int)pp[15]), max((int)pp[16], (int)pp[17])), (int)pp[18]));
-    if (mx >= high)            // demod_2400.rs:135-146
-        return;
-    const int jl = mi - kHaloFront;
-    atomicOr(&surv[jl >> 5], 1u << (jl & 31));
-}
-
 // ------------------------------------------------------------------ preamble templates
 // plane[rho][w] bit b  <->  tile mag index 12*(32w+b)+rho.  term(s) returns, for the 32
 // positions of item (rho, w), the plane bit of index position+s.
@@ -390,7 +409,73 @@ __device__ __forceinline__ uint32_t plane_term(const uint32_t *plane, int WP, in
 // padded to 396 words; the 12 pad words repeat the next block's first 12, so a lane that
 // walks one residue class (i = 12q + rho, q = 32 consecutive) reads d[i..i+2] with plain
 // strides and 32 consecutive (block, rho) items hit 32 different banks.
-__device__ __forceinline__ int dd_pos(int i) { return kDDBlock * (i / kStep) + (i % kStep); }
+
+// eight consecutive IQ words of a buffer starting at sample s (zero outside [0, len):
+// magnitude(0, 0) = 0 is exactly the MagnitudeBuffer zero fill, lib.rs:36-44)
+__device__ __forceinline__ void load_iq8(const uint32_t *b32, int s, int len, int vec_ok, uint32_t w[8])
+{
+    if (s >= 0 && s + 7 < len && vec_ok) {
+        const int4 v0 = __ldg(reinterpret_cast<const int4 *>(b32 + s));
+        const int4 v1 = __ldg(reinterpret_cast<const int4 *>(b32 + s + 4));
+        w[0] = (uint32_t)v0.x; w[1] = (uint32_t)v0.y; w[2] = (uint32_t)v0.z; w[3] = (uint32_t)v0.w;
+        w[4] = (uint32_t)v1.x; w[5] = (uint32_t)v1.y; w[6] = (uint32_t)v1.z; w[7] = (uint32_t)v1.w;
+    } else {
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int se = s + e;
+            w[e] = (se >= 0 && se < len) ? __ldg(b32 + se) : 0u;
+        }
+    }
+}
+
+// SNR and quiet-zone gates of one template match (demod_2400.rs:129,135-146) with the
+// template's high/signal/noise (demod_2400.rs:226-317); cs = template case 0..4.
+__device__ __forceinline__ void gate_eval(const uint16_t *mag, uint32_t *surv, int mi, uint32_t cs)
+{
+    const uint16_t *pp = mag + mi;
+    int high;
+    uint32_t sig, noise;
+    switch (cs) {
+    case 0:
+        high = ((int)pp[1] + pp[3] + pp[9] + pp[11] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[3] + pp[9];
+        noise = (uint32_t)pp[5] + pp[6] + pp[7];
+        break;
+    case 1:
+        high = ((int)pp[1] + pp[3] + pp[9] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[3] + pp[9] + pp[12];
+        noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
+        break;
+    case 2:
+        high = ((int)pp[1] + pp[3] + pp[4] + pp[9] + pp[10] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[12];
+        noise = (uint32_t)pp[6] + pp[7];
+        break;
+    case 3:
+        high = ((int)pp[1] + pp[4] + pp[10] + pp[12]) / 4;
+        sig = (uint32_t)pp[1] + pp[4] + pp[10] + pp[12];
+        noise = (uint32_t)pp[5] + pp[6] + pp[7] + pp[8];
+        break;
+    default:
+        high = ((int)pp[1] + pp[2] + pp[4] + pp[10] + pp[12]) / 4;
+        sig = (uint32_t)pp[4] + pp[10] + pp[12];
+        noise = (uint32_t)pp[6] + pp[7] + pp[8];
+        break;
+    }
+    if (sig * 2 < 3 * noise)   // demod_2400.rs:129
+        return;
+    const int mx = max(max(max((int)pp[5], (int)pp[6]), max((int)pp[7], (int)pp[8])),
+                       max(max(max((int)pp[14], (int)pp[15]), max((int)pp[16], (int)pp[17])), (int)pp[18]));
+    if (mx >= high)            // demod_2400.rs:135-146
+        return;
+    const int jl = mi - kHaloFront;
+    atomicOr(&surv[jl >> 5], 1u << (jl & 31));
+}
+
+__device__ __forceinline__ uint32_t df_of_fields(const uint32_t f[5])
+{
+    return ((f[0] & 1u) << 4) | ((f[1] & 1u) << 3) | ((f[2] & 1u) << 2) | ((f[3] & 1u) << 1) | (f[4] & 1u);
+}
 
 template <bool FROM_MAG>
 __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
@@ -399,13 +484,14 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     const ScanSmem L(p.T);
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
     int *dd = reinterpret_cast<int *>(smem + L.off_dd);
+    uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd is dead)
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [7][12][WP]
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
-    uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);
+    uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);     // [5][kQueueCap]
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
     __shared__ uint32_t s_warp_tot[kWarps];
-    __shared__ uint32_t s_base, s_count, s_ok, s_qn;
+    __shared__ uint32_t s_base, s_count, s_ok, s_qn[5], s_nlong, s_nshort;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -423,67 +509,60 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     const int MPe = steps * kStep;
     const int WP = L.WP;
 
-    // ---- P1: magnitudes m[0, MPe+8) (u16) and differences d[0, MPe+4) (i32) -> shared memory.
-    // A warp takes 256 consecutive samples per iteration, 8 per lane (two 16-byte loads).
+    // ---- P1: magnitudes m[0, MPe+8) (u16) and differences d[0, MPe+12) (i32) -> shared memory.
+    // A warp takes 248 new samples per iteration, 8 per lane; lane 31 recomputes the next
+    // chunk's first 8 only to hand lane 30 its right neighbour.
     {
-        const int nchunk = (MPe + 8 + kChunk - 1) / kChunk;
+        const int nchunk = (MPe + 16 + kChunk - 1) / kChunk;
         const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of m[0]
         const int i0 = tile_start - kHaloFront;                  // data index of m[0]
+        const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
+        const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
+        uint32_t wn[8];
+        if (!FROM_MAG && warp < nchunk)
+            load_iq8(b32, s0 + warp * kChunk + 8 * lane, len, p.vec_ok, wn);
         for (int ch = warp; ch < nchunk; ch += kWarps) {
             const int mi = ch * kChunk + 8 * lane;
             uint32_t r[9];   // 0x4B000000 + magnitude
             if (!FROM_MAG) {
-                const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
-                const int s = s0 + mi;
-                if (s >= 0 && s + 7 < len && p.vec_ok) {
-                    const int4 v0 = __ldg(reinterpret_cast<const int4 *>(b32 + s));
-                    const int4 v1 = __ldg(reinterpret_cast<const int4 *>(b32 + s + 4));
-                    r[0] = mag_bits_fast((uint32_t)v0.x);
-                    r[1] = mag_bits_fast((uint32_t)v0.y);
-                    r[2] = mag_bits_fast((uint32_t)v0.z);
-                    r[3] = mag_bits_fast((uint32_t)v0.w);
-                    r[4] = mag_bits_fast((uint32_t)v1.x);
-                    r[5] = mag_bits_fast((uint32_t)v1.y);
-                    r[6] = mag_bits_fast((uint32_t)v1.z);
-                    r[7] = mag_bits_fast((uint32_t)v1.w);
-                } else {
+                uint32_t w[8];
 #pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const int se = s + e;
-                        r[e] = (se >= 0 && se < len) ? mag_bits_fast(__ldg(b32 + se)) : 0x4B000000u;
-                    }
-                }
-                r[8] = __shfl_down_sync(0xffffffffu, r[0], 1);
-                if (lane == 31) {
-                    const int se = s + 8;
-                    r[8] = (se >= 0 && se < len) ? mag_bits_fast(__ldg(b32 + se)) : 0x4B000000u;
-                }
+                for (int e = 0; e < 8; e++)
+                    w[e] = wn[e];
+                if (ch + kWarps < nchunk)   // next chunk's loads fly while this one computes
+                    load_iq8(b32, s0 + (ch + kWarps) * kChunk + 8 * lane, len, p.vec_ok, wn);
+                mag_bits_fast2(w[0], w[1], r[0], r[1]);
+                mag_bits_fast2(w[2], w[3], r[2], r[3]);
+                mag_bits_fast2(w[4], w[5], r[4], r[5]);
+                mag_bits_fast2(w[6], w[7], r[6], r[7]);
             } else {
-                const uint16_t *d = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
 #pragma unroll
-                for (int e = 0; e < 9; e++) {
+                for (int e = 0; e < 8; e++) {
                     const int idx = i0 + mi + e;
-                    r[e] = 0x4B000000u + ((idx >= 0 && idx < kMagLen) ? (uint32_t)__ldg(d + idx) : 0u);
+                    r[e] = 0x4B000000u + ((idx >= 0 && idx < kMagLen) ? (uint32_t)__ldg(d16 + idx) : 0u);
                 }
             }
-            // u16 magnitudes, 8 per lane
-            *reinterpret_cast<uint4 *>(mag + mi) =
-                make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410),
-                           __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
-            // first differences (bit patterns share the binade, so they subtract like integers)
-            int dv[8];
+            r[8] = __shfl_down_sync(0xffffffffu, r[0], 1);
+            if (lane < 31) {
+                // u16 magnitudes, 8 per lane
+                *reinterpret_cast<uint4 *>(mag + mi) =
+                    make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410),
+                               __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
+                // first differences (the bit patterns share a binade: they subtract like integers)
+                int dv[8];
 #pragma unroll
-            for (int e = 0; e < 8; e++)
-                dv[e] = (int)(r[e + 1] - r[e]);
-            const int blk = mi / kStep, off = mi - blk * kStep;
-            int *dst = dd + kDDBlock * blk + off;
-            *reinterpret_cast<int4 *>(dst) = make_int4(dv[0], dv[1], dv[2], dv[3]);
-            *reinterpret_cast<int4 *>(dst + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
-            if (off < 12 && blk > 0) {   // mirror into the previous block's pad
-                int *pad = dd + kDDBlock * (blk - 1) + kStep + off;
-                *reinterpret_cast<int4 *>(pad) = make_int4(dv[0], dv[1], dv[2], dv[3]);
-                if (off == 0)
-                    *reinterpret_cast<int4 *>(pad + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
+                for (int e = 0; e < 8; e++)
+                    dv[e] = (int)(r[e + 1] - r[e]);
+                const int blk = mi / kStep, off = mi - blk * kStep;
+                int *dst = dd + kDDBlock * blk + off;
+                *reinterpret_cast<int4 *>(dst) = make_int4(dv[0], dv[1], dv[2], dv[3]);
+                *reinterpret_cast<int4 *>(dst + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
+                if (off < 12 && blk > 0) {   // mirror into the previous block's pad
+                    int *pad = dd + kDDBlock * (blk - 1) + kStep + off;
+                    *reinterpret_cast<int4 *>(pad) = make_int4(dv[0], dv[1], dv[2], dv[3]);
+                    if (off == 0)
+                        *reinterpret_cast<int4 *>(pad + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
+                }
             }
         }
     }
@@ -493,8 +572,8 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
         tabs[c] = __ldg(p.crc_tabs + c);
     for (int c = tid; c < 7 * 12; c += kThreads)
         planes[c * WP + steps] = 0;   // pad word read by funnel shifts
-    if (tid == 0)
-        s_qn = 0;
+    if (tid < 5)
+        s_qn[tid] = 0;
     __syncthreads();
 
     // ---- P2: bit planes.  One lane = one residue class rho of one 384-block: 32 samples at
@@ -531,7 +610,8 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     }
     __syncthreads();
 
-    // ---- P3a: preamble templates, 32 positions per item; matches go to a queue
+    // ---- P3a: preamble templates, 32 positions per item; matches go to one queue per
+    // template case
     {
         const uint32_t *R = planes + 5 * 12 * WP, *F = planes + 6 * 12 * WP;
         for (int item = tid; item < 12 * steps; item += kThreads) {
@@ -552,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             const uint32_t R2 = plane_term(R, WP, rho, w, 2), R3 = plane_term(R, WP, rho, w, 3),
                            R8 = plane_term(R, WP, rho, w, 8), R9 = plane_term(R, WP, rho, w, 9),
                            R10 = plane_term(R, WP, rho, w, 10), R11 = plane_term(R, WP, rho, w, 11);
-            // demod_2400.rs:226-317, in order
+            // demod_2400.rs:226-317, in order; first match wins
             const uint32_t T3 = F1 & R2 & F3 & R8 & F9 & R10;
             const uint32_t T4 = F1 & R2 & F3 & R8 & F9 & R11;
             const uint32_t T5 = F1 & R2 & F4 & R8 & F10 & R11;
@@ -561,29 +641,43 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             uint32_t any = quick & (T3 | T4 | T5 | T6 | T7);
             if (!any)
                 continue;
-            const uint32_t c0 = T3, c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5);
-            uint32_t qi = atomicAdd(&s_qn, (uint32_t)__popc(any));
+            // case number as three bit planes: 0:T3 1:T4 2:T5 3:T6 4:T7
+            const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5),
+                           c4 = ~(T3 | T4 | T5 | T6);
+            const uint32_t b0 = c1 | c3, b1 = c2 | c3;
+            const int mi0 = 12 * 32 * w + rho;
             while (any) {
                 const int bit = __ffs(any) - 1;
                 any &= any - 1;
-                const uint32_t cs = ((c0 >> bit) & 1u) ? 0u : ((c1 >> bit) & 1u) ? 1u : ((c2 >> bit) & 1u) ? 2u
-                                    : ((c3 >> bit) & 1u) ? 3u : 4u;
-                const uint32_t mi = (uint32_t)(12 * (32 * w + bit) + rho);
-                const uint32_t e = mi | (cs << 13);
+                const uint32_t cs = ((b0 >> bit) & 1u) | (((b1 >> bit) & 1u) << 1) | (((c4 >> bit) & 1u) << 2);
+                const int mi = mi0 + 12 * bit;
+                const uint32_t qi = atomicAdd(&s_qn[cs], 1u);
                 if (qi < (uint32_t)kQueueCap)
-                    queue[qi] = (uint16_t)e;
+                    queue[cs * kQueueCap + qi] = (uint16_t)mi;
                 else
-                    gate_eval(mag, surv, e);     // queue full: evaluate in place
-                qi++;
+                    gate_eval(mag, surv, mi, cs);     // queue full: evaluate in place
             }
         }
     }
     __syncthreads();
-    // ---- P3b: SNR and quiet-zone gates, one queue entry per thread
+    // ---- P3b: SNR and quiet-zone gates, one queue entry per thread, queues back to back
     {
-        const int qn = (int)min(s_qn, (uint32_t)kQueueCap);
-        for (int i = tid; i < qn; i += kThreads)
-            gate_eval(mag, surv, queue[i]);
+        int n[5], tot = 0;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+            n[c] = (int)min(s_qn[c], (uint32_t)kQueueCap);
+            tot += n[c];
+        }
+        for (int g = tid; g < tot; g += kThreads) {
+            int cs = 0, idx = g;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (cs == c && idx >= n[c]) {
+                    idx -= n[c];
+                    cs = c + 1;
+                }
+            gate_eval(mag, surv, (int)queue[cs * kQueueCap + idx], (uint32_t)cs);
+        }
     }
     __syncthreads();
 
@@ -625,14 +719,18 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             s_base = base;
             s_count = total;
             s_ok = ok;
+            s_nlong = 0;
+            s_nshort = 0;
         }
     }
     __syncthreads();
     if (!s_ok || s_count == 0)
         return;
 
-    // ---- P4b: five try-phases per survivor -> record words + ICAO add-events,
-    // in windows of kCandCap survivors
+    // ---- P4b: five try-phases per survivor, in windows of kCandCap survivors.
+    //   A: pull the five 23-bit fields of each (survivor, try_phase) out of the sign planes,
+    //      read the DF; items that need a CRC are staged by class (112-bit / 56-bit syndrome)
+    //   B: CRC-24 + classification on class-homogeneous runs -> record words + ICAO add-events
     const int C = (int)s_count;
     const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
     for (int win = 0; win < C; win += kCandCap) {
@@ -649,33 +747,96 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
         }
         __syncthreads();
         const int Cw = min(kCandCap, C - win);
+        uint32_t *rec_w = p.rec + 6ull * (s_base + (uint32_t)win);
         for (int item = tid; item < 5 * Cw; item += kThreads) {
             const int c = item / 5, tt = item - 5 * c;
             const int jl = cand[c];
-            const int P0 = 5 * (jl + kHaloFront + 19) + 4 + tt;   // demod_2400.rs:158-160
+            // demod_2400.rs:158-160: P0 = 5*(mi+19) + try_phase, try_phase = 4+tt
+            const int A = jl + kHaloFront + 19;
+            const int qA = A / 12, rA = A - 12 * qA;
+            const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
             uint32_t f[5];
 #pragma unroll
             for (int r = 0; r < 5; r++) {
-                const int Pr = P0 + 12 * r;
-                const int i = Pr / 5, phi = Pr - 5 * i;
-                const int q = i / 12, rho = i - 12 * q;
+                const int z = phi0 + 12 * r;            // P_r = 5*(A+e5) + z
+                const int zd = (z * 205) >> 10;         // z / 5 for z < 64
+                const int phi = z - 5 * zd;
+                int rho = rA + e5 + zd, q = qA;         // sample A+e5+zd = 12q + rho
+                if (rho >= 12) {
+                    rho -= 12;
+                    q++;
+                }
                 const uint32_t *st = planes + (phi * 12 + rho) * WP + (q >> 5);
                 f[r] = __funnelshift_r(st[0], st[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
             }
-            const uint32_t wd = classify_fields(tabs, f);
-            const uint32_t kind = wd >> 29;
-            const uint32_t j = (uint32_t)(tile_start + jl);
-            uint32_t *rec = p.rec + 6ull * (s_base + (uint32_t)(win + c));
-            rec[1 + tt] = wd;
             if (tt == 0)
-                rec[0] = j;
-            if (kind == K_DF11_IID0 || kind == K_DF17 || kind == K_DF18) {
-                const uint32_t key = (wd & 0xffffffu) | (kind == K_DF18 ? B200ADSB_ICAO_FILTER_ADSB_NT : 0u);
-                event_add(p.ev_keys, p.ev_ord, p.ev_used, p.ev_mask, p.counters, key,
-                          ord_buf | ((unsigned long long)j << 3) | (unsigned long long)tt);
+                rec_w[6 * c] = (uint32_t)(tile_start + jl);
+            uint32_t wd = 0;
+            bool staged = false;
+            if ((f[0] | f[1] | f[2] | f[3] | f[4]) == 0) {
+                wd = kNoneMarker;                      // all 14 bytes zero -> None (mode_s/mod.rs:51-53)
+            } else {
+                const uint32_t bit = 1u << df_of_fields(f);
+                const bool is_long = (bit & 0xFF370000u) != 0;    // DF 16,17,18,20,21,24..31
+                const bool is_short = (bit & 0x00000831u) != 0;   // DF 0,4,5,11
+                if (is_long || is_short) {
+                    const uint32_t slot = is_long ? atomicAdd(&s_nlong, 1u)
+                                                  : (uint32_t)(kFieldItems - 1) - atomicAdd(&s_nshort, 1u);
+                    uint32_t *o = fb + 5 * slot;
+                    o[0] = f[0];
+                    o[1] = f[1];
+                    o[2] = f[2] | (((uint32_t)item & 0x3ffu) << 22);
+                    o[3] = f[3] | (((uint32_t)item >> 10) << 22);
+                    o[4] = f[4];
+                    staged = true;
+                }
+            }
+            if (!staged)
+                rec_w[6 * c + 1 + tt] = wd;
+        }
+        __syncthreads();
+        {
+            const int nl = (int)s_nlong, ns = (int)s_nshort;
+            for (int g = tid; g < nl + ns; g += kThreads) {
+                const bool is_long = g < nl;
+                const uint32_t slot = is_long ? (uint32_t)g : (uint32_t)(kFieldItems - 1 - (g - nl));
+                const uint32_t *o = fb + 5 * slot;
+                uint32_t f[5] = {o[0], o[1], o[2], o[3], o[4]};
+                const int item = (int)((f[2] >> 22) | ((f[3] >> 22) << 10));
+                f[2] &= 0x3fffffu;
+                f[3] &= 0x3fffffu;
+                const uint32_t df = df_of_fields(f);
+                uint32_t wd;
+                if (is_long) {
+                    const uint32_t syn = syn112_fields(tabs, f);
+                    if (df == 17 || df == 18)          // mode_s/mod.rs:91-109
+                        wd = syn ? 0u : (((df == 17 ? K_DF17 : K_DF18) << 29) | msg_bits<8, 24>(f));
+                    else                                // :110-134
+                        wd = (K_PAR_LONG << 29) | syn;
+                } else {
+                    const uint32_t syn = syn56_fields(tabs, f);
+                    if (df == 11)                       // :73-90
+                        wd = (syn & 0xffff80u) ? 0u
+                                               : ((((syn & 0x7f) ? K_DF11_IID : K_DF11_IID0) << 29) | msg_bits<8, 24>(f));
+                    else                                // :56-72
+                        wd = (K_PAR_SHORT << 29) | syn;
+                }
+                const int c = item / 5, tt = item - 5 * c;
+                rec_w[6 * c + 1 + tt] = wd;
+                const uint32_t kind = wd >> 29;
+                if (kind == K_DF11_IID0 || kind == K_DF17 || kind == K_DF18) {
+                    const uint32_t key = (wd & 0xffffffu) | (kind == K_DF18 ? B200ADSB_ICAO_FILTER_ADSB_NT : 0u);
+                    const uint32_t j = (uint32_t)(tile_start + cand[c]);
+                    event_add(p.ev_keys, p.ev_ord, p.ev_used, p.ev_mask, p.counters, key,
+                              ord_buf | ((unsigned long long)j << 3) | (unsigned long long)tt);
+                }
             }
         }
         __syncthreads();
+        if (tid == 0) {
+            s_nlong = 0;
+            s_nshort = 0;
+        }
     }
 }
 
