@@ -152,7 +152,7 @@ def main() -> int:
     import numpy as np
     import torch
     import dump1090_rs_b200 as d
-    from dump1090_rs_b200 import _ffi, synth
+    from dump1090_rs_b200 import _ffi, sharded, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -181,26 +181,18 @@ def main() -> int:
         ctx.set_option(_ffi.OPT_TILE, args.tile)
     cap = 1 << 16
     frames = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
-    pairs = torch.zeros((4096, 2), dtype=torch.int64, device=dev)
     n_frames = [0]
+
+    sh = sharded.ShardedDemodulator(ctx, rank, world) if world > 1 else None
 
     def step_device():
         ctx.icao_flush()
         if world == 1:
             n_frames[0] = ctx.demod_iq_batch_ptr(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap)
-            return
-        ctx.scan_batch_dev(iq.data_ptr(), nb, SAMPLES, SAMPLES, rank, world)
-        n_ev = ctx.events_export_dev(pairs.data_ptr(), 4096)
-        cnt = torch.tensor([n_ev], dtype=torch.int64, device=dev)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        gathered = [torch.zeros_like(pairs) for _ in range(world)]
-        dist.all_gather(gathered, pairs)
-        for r in range(world):
-            if r != rank and int(cnts[r]) > 0:
-                ctx.events_import_dev(gathered[r].data_ptr(), int(cnts[r]))
-        torch.cuda.current_stream().synchronize()
-        n_frames[0] = ctx.resolve_batch_dev(frames.data_ptr(), cap)
+        else:
+            # scan -> all-gather of ICAO add-events (NCCL) -> resolve
+            sh.position = 0
+            n_frames[0] = sh.step(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap)
 
     def barrier():
         if dist is not None:

@@ -1,0 +1,82 @@
+"""One stream dealt round-robin over several GPUs (BASELINE.json configs[4]).
+
+The sample-domain work has no dependency between IQ buffers (utils.rs:44, lib.rs:47-50), so
+buffer g of the stream goes to rank g % world.  The one thing the reference shares between
+buffers is the ICAO address filter (icao_filter.rs:8-9).  Its evolution is order-free once
+every rank knows, for every address, the earliest stream position that adds it
+(SURVEY.md A.6), so the exchange step is one tiny all-gather of (key, ordinal) pairs
+between the scan and the resolve stages -- a few entries per buffer.
+
+torch.distributed is the plumbing only (NCCL on GPUs; the same code runs on gloo/CPU
+tensors in tests/test_sharded_gloo.py).
+"""
+from __future__ import annotations
+
+
+def owner_of(global_buffer: int, world: int) -> tuple[int, int]:
+    """(rank, local index) of stream buffer g under round-robin dealing."""
+    return global_buffer % world, global_buffer // world
+
+
+def local_buffers(n_total: int, world: int, rank: int) -> list[int]:
+    """Global indices of the buffers rank `rank` owns, in local order."""
+    return list(range(rank, n_total, world))
+
+
+def exchange_events(pairs, count: int, group=None):
+    """All-gather the ranks' ICAO add-events.
+
+    pairs: int64 tensor [cap, 2] holding (key, ordinal) rows, the first `count` valid, on
+    the device the backend works with.  Returns (remote, n_remote): the other ranks' valid
+    rows concatenated ([m, 2]).  With world size 1 returns an empty tensor.
+    """
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return pairs[:0], 0
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    cnt = torch.tensor([count], dtype=torch.int64, device=pairs.device)
+    cnts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(cnts, cnt, group=group)
+    counts = [int(c.item()) for c in cnts]
+    width = max(max(counts), 1)
+    send = torch.zeros((width, 2), dtype=torch.int64, device=pairs.device)
+    send[:count] = pairs[:count]
+    gathered = [torch.zeros_like(send) for _ in range(world)]
+    dist.all_gather(gathered, send, group=group)
+    rows = [gathered[r][:counts[r]] for r in range(world) if r != rank and counts[r]]
+    if not rows:
+        return pairs[:0], 0
+    remote = torch.cat(rows).contiguous()
+    return remote, remote.shape[0]
+
+
+class ShardedDemodulator:
+    """This rank's share of a sharded stream: scan -> exchange -> resolve on its Context."""
+
+    def __init__(self, ctx, rank: int, world: int, group=None, event_cap: int = 4096):
+        import torch
+
+        self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
+        self.event_cap = event_cap
+        self.pairs = torch.zeros((event_cap, 2), dtype=torch.int64, device=torch.device("cuda", ctx.device))
+        self.position = 0          # stream position (in global buffers) of the next batch
+
+    def step(self, iq_ptr: int, n_local: int, spb: int, stride: int, out_ptr: int, cap: int,
+             n_total: int | None = None, counts_ptr: int = 0) -> int:
+        """Demodulates this rank's n_local buffers of a batch of n_total stream buffers
+        (default n_local * world); frames (with local buffer indices) go to out_ptr."""
+        import torch
+
+        n_total = n_local * self.world if n_total is None else n_total
+        self.ctx.scan_batch_dev(iq_ptr, n_local, spb, stride, self.position + self.rank, self.world)
+        n_ev = self.ctx.events_export_dev(self.pairs.data_ptr(), self.event_cap)
+        remote, m = exchange_events(self.pairs, n_ev, self.group)
+        if m:
+            torch.cuda.current_stream().synchronize()
+            self.ctx.events_import_dev(remote.data_ptr(), m)
+            self.ctx.sync()
+        n = self.ctx.resolve_batch_dev(out_ptr, cap, counts_ptr)
+        self.position += n_total
+        return n

@@ -343,3 +343,23 @@ def test_split_scan_resolve_two_shards(pkg, oracle_mod):
     for r in range(2):
         assert set(ctxs[r].icao_snapshot()) == o.members()
         ctxs[r].close()
+
+
+def test_cpp_host_mirror_reference_routine(tmp_path, captures, golden_frames):
+    """The C++ mirror of the crate surface (dump1090_rs_b200/host/dump1090_rs.hpp) running the
+    reference's own routine (tests/test.rs:7-17) on a capture file in the reference's on-disk
+    format, compared with the golden vectors."""
+    import os
+    import subprocess
+    from dump1090_rs_b200 import utils
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(here, "dump1090_rs_b200", "host")
+    exe = os.path.join(host, "reference_routine")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, os.path.join(host, "reference_routine.cpp"),
+                               "-L" + os.path.join(here, "dump1090_rs_b200"), "-lb200adsb", "-Wl,-rpath,$ORIGIN/.."])
+    name = NAMES[2]
+    path = utils.save_test_data(captures[name], str(tmp_path / (name + ".iq")))
+    assert np.array_equal(utils.read_test_data(path), captures[name])
+    out = subprocess.run([exe, path], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["*" + g["hex"] + ";" for g in golden_frames[name]]

@@ -87,52 +87,7 @@ def test_filter_semantics(oracle_mod):
     assert oracle_mod.icao_hash(0) == 0
 
 
-def resolve_records(records_per_buffer, preloaded=frozenset(), capacity=4096, ordinals=None):
-    """Order-free evaluation of the ICAO filter used by the CUDA path,
-    restated in Python for the tests: returns per buffer [(j, phase, score, len)], and
-    the final member set."""
-    K_NONE, K_PS, K_11Z, K_11I, K_17, K_18, K_PL = range(7)
-    first = {}
-    for b, recs in enumerate(records_per_buffer):
-        ob = b if ordinals is None else ordinals[b]
-        for j, w in recs:
-            for t, wd in enumerate(w):
-                kind, key = wd >> 29, wd & 0xFFFFFF
-                if kind in (K_11Z, K_17, K_18):
-                    k = key | ((1 << 25) if kind == K_18 else 0)
-                    if k == 0:
-                        continue
-                    o = (ob, j, t)
-                    if k not in first or o < first[k]:
-                        first[k] = o
-    # DF18 adds addr|ADSB_NT only while icao_filter_test(addr) is still false
-    for k in [k for k in first if k >> 25]:
-        plain = k & 0xFFFFFF
-        if plain in preloaded or (plain in first and first[plain] < first[k]):
-            del first[k]
-    new = sorted((o, k) for k, o in first.items() if k not in preloaded)
-    room = capacity - len(preloaded)
-    admitted = {k: o for o, k in new[:max(room, 0)]}
-    out = []
-    for b, recs in enumerate(records_per_buffer):
-        ob = b if ordinals is None else ordinals[b]
-        res = []
-        for j, w in recs:
-            best, bt, bl = -2, 0, 7
-            for t, wd in enumerate(w):
-                kind, key = wd >> 29, wd & 0xFFFFFF
-                if kind == K_NONE:
-                    continue
-                m = key == 0 or key in preloaded or (key in admitted and admitted[key] < (ob, j, t))
-                score, ln = {K_PS: (1000 if m else -1, 7), K_11Z: (1600 if m else 750, 7),
-                             K_11I: (1000 if m else -1, 7), K_17: (1800 if m else 1400, 14),
-                             K_18: (1800 if m else 1400, 14), K_PL: (1000 if m else -2, 14)}[kind]
-                if score > best:
-                    best, bt, bl = score, t, ln
-            if best >= 0:
-                res.append((j, 4 + bt, best, bl))
-        out.append(res)
-    return out, set(preloaded) | set(admitted)
+from filter_model import resolve_records  # noqa: E402
 
 
 def test_two_pass_equals_sequential(captures, oracle_mod):
