@@ -89,7 +89,7 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 // shared memory plan of the scan kernel for tile size T
 struct ScanSmem {
     int steps, MP, MPc, WP, nw, dd_words;
-    size_t off_dd, off_planes, off_surv, off_tabs, off_queue, off_cand, bytes;
+    size_t off_dd, off_planes, off_edges, off_surv, off_tabs, off_queue, off_cand, bytes;
     __host__ __device__ explicit ScanSmem(int T)
     {
         steps = (T + kHaloTot + kStep - 1) / kStep;   // 384-sample blocks (12 residues x 32)
@@ -104,8 +104,11 @@ struct ScanSmem {
         if (dd_words < kFieldItems * 5)               // later reused as the P4 field buffer
             dd_words = kFieldItems * 5;
         o += (size_t)dd_words * 4;
-        off_planes = o;
-        o += (size_t)7 * 12 * WP * 4;
+        off_planes = o;                               // S[phi][rho][word], de-interleaved mod 12
+        o += (size_t)5 * 12 * WP * 4;
+        off_edges = o;                                // R then F: one bit per sample, consecutive
+        o += (size_t)2 * (MPc / 8 + 16);
+        o = (o + 15) & ~(size_t)15;
         off_surv = o;
         o += (size_t)nw * 4;
         off_tabs = o;
@@ -485,13 +488,15 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
     int *dd = reinterpret_cast<int *>(smem + L.off_dd);
     uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd is dead)
-    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [7][12][WP]
+    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [5][12][WP]
+    uint8_t *Rc = smem + L.off_edges;                 // rising-edge bit of every sample (bit i <-> m[i] < m[i+1])
+    uint8_t *Fc = Rc + (L.MPc / 8 + 16);              // falling-edge bit
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);     // [5][kQueueCap]
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
     __shared__ uint32_t s_warp_tot[kWarps];
-    __shared__ uint32_t s_base, s_count, s_ok, s_qn[5], s_nlong, s_nshort;
+    __shared__ uint32_t s_base, s_count, s_ok, s_qn[5], s_nlong, s_nshort, s_lut[25];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -553,6 +558,15 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
 #pragma unroll
                 for (int e = 0; e < 8; e++)
                     dv[e] = (int)(r[e + 1] - r[e]);
+                // edge bits of these 8 samples (demod_2400.rs:221-317 compares neighbours only)
+                uint32_t fbits = 0, rbits = 0;
+#pragma unroll
+                for (int e = 7; e >= 0; e--) {
+                    fbits = __funnelshift_l((uint32_t)dv[e], fbits, 1);      // m[i+1]-m[i] < 0: falling
+                    rbits = __funnelshift_l((uint32_t)(-dv[e]), rbits, 1);   // rising
+                }
+                Fc[mi >> 3] = (uint8_t)fbits;
+                Rc[mi >> 3] = (uint8_t)rbits;
                 const int blk = mi / kStep, off = mi - blk * kStep;
                 int *dst = dd + kDDBlock * blk + off;
                 *reinterpret_cast<int4 *>(dst) = make_int4(dv[0], dv[1], dv[2], dv[3]);
@@ -570,10 +584,18 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
         surv[c] = 0;
     for (int c = tid; c < kTabWords; c += kThreads)
         tabs[c] = __ldg(p.crc_tabs + c);
-    for (int c = tid; c < 7 * 12; c += kThreads)
+    for (int c = tid; c < 5 * 12; c += kThreads)
         planes[c * WP + steps] = 0;   // pad word read by funnel shifts
     if (tid < 5)
         s_qn[tid] = 0;
+    if (tid < 25) {
+        // field r of try-phase 4+tt starts at 1/5-sample position 5*(A+e5)+z (A = j+19):
+        // sample offset delta from A and plane base of its correlator phi
+        const int tt = tid / 5, r = tid - 5 * tt;
+        const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
+        const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
+        s_lut[tid] = (uint32_t)(e5 + zd) | ((uint32_t)(phi * 12 * WP) << 8);
+    }
     __syncthreads();
 
     // ---- P2: bit planes.  One lane = one residue class rho of one 384-block: 32 samples at
@@ -585,7 +607,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     for (int item = tid; item < 12 * steps; item += kThreads) {
         const int blk = item / 12, rho = item - 12 * blk;
         const int *dp = dd + kDDBlock * blk + rho;
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, ar = 0, af = 0;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
 #pragma unroll
         for (int q = 31; q >= 0; q--) {
             const int u = dp[12 * q], v = dp[12 * q + 1], w = dp[12 * q + 2];
@@ -596,8 +618,6 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             a2 = __funnelshift_l((uint32_t)x2, a2, 1);
             a3 = __funnelshift_l((uint32_t)x3, a3, 1);
             a4 = __funnelshift_l((uint32_t)x4, a4, 1);
-            af = __funnelshift_l((uint32_t)u, af, 1);      // m[i+1]-m[i] < 0: falling
-            ar = __funnelshift_l((uint32_t)(-u), ar, 1);   // rising
         }
         uint32_t *pl = planes + rho * WP + blk;
         pl[0 * 12 * WP] = a0;
@@ -605,33 +625,30 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
         pl[2 * 12 * WP] = a2;
         pl[3 * 12 * WP] = a3;
         pl[4 * 12 * WP] = a4;
-        pl[5 * 12 * WP] = ar;
-        pl[6 * 12 * WP] = af;
     }
     __syncthreads();
 
-    // ---- P3a: preamble templates, 32 positions per item; matches go to one queue per
-    // template case
+    // ---- P3a: preamble templates on the edge bitmaps, 32 consecutive positions per thread;
+    // matches go to one queue per template case
     {
-        const uint32_t *R = planes + 5 * 12 * WP, *F = planes + 6 * 12 * WP;
-        for (int item = tid; item < 12 * steps; item += kThreads) {
-            const int w = item / 12, rho = item - 12 * w;
-            // valid positions: 2 <= mi < npos+2 with mi = 12*(32w+bit)+rho
-            const int q_lo = (rho < kHaloFront) ? 1 : 0;
-            const int q_hi = (npos + kHaloFront - rho + 11) / 12;   // exclusive
-            const int lo = max(q_lo - 32 * w, 0), hi = min(q_hi - 32 * w, 32);
-            if (hi <= lo)
-                continue;
+        const uint32_t *R32 = reinterpret_cast<const uint32_t *>(Rc), *F32 = reinterpret_cast<const uint32_t *>(Fc);
+        const int nwp = (npos + kHaloFront + 31) / 32;
+        for (int w = tid; w < nwp; w += kThreads) {
+            // valid positions: 2 <= mi < npos+2 with mi = 32w + bit
+            const int lo = max(kHaloFront - 32 * w, 0), hi = min(npos + kHaloFront - 32 * w, 32);
             const uint32_t valid = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-            const uint32_t quick = plane_term(R, WP, rho, w, 0) & plane_term(F, WP, rho, w, 12) & valid;
+            const uint32_t r0 = R32[w], r1 = R32[w + 1], f0 = F32[w], f1 = F32[w + 1];
+#define EDGE_R(s) __funnelshift_r(r0, r1, s)
+#define EDGE_F(s) __funnelshift_r(f0, f1, s)
+            const uint32_t quick = r0 & EDGE_F(12) & valid;   // demod_2400.rs:221
             if (!quick)
                 continue;
-            const uint32_t F1 = plane_term(F, WP, rho, w, 1), F2 = plane_term(F, WP, rho, w, 2),
-                           F3 = plane_term(F, WP, rho, w, 3), F4 = plane_term(F, WP, rho, w, 4),
-                           F9 = plane_term(F, WP, rho, w, 9), F10 = plane_term(F, WP, rho, w, 10);
-            const uint32_t R2 = plane_term(R, WP, rho, w, 2), R3 = plane_term(R, WP, rho, w, 3),
-                           R8 = plane_term(R, WP, rho, w, 8), R9 = plane_term(R, WP, rho, w, 9),
-                           R10 = plane_term(R, WP, rho, w, 10), R11 = plane_term(R, WP, rho, w, 11);
+            const uint32_t F1 = EDGE_F(1), F2 = EDGE_F(2), F3 = EDGE_F(3), F4 = EDGE_F(4), F9 = EDGE_F(9),
+                           F10 = EDGE_F(10);
+            const uint32_t R2 = EDGE_R(2), R3 = EDGE_R(3), R8 = EDGE_R(8), R9 = EDGE_R(9), R10 = EDGE_R(10),
+                           R11 = EDGE_R(11);
+#undef EDGE_R
+#undef EDGE_F
             // demod_2400.rs:226-317, in order; first match wins
             const uint32_t T3 = F1 & R2 & F3 & R8 & F9 & R10;
             const uint32_t T4 = F1 & R2 & F3 & R8 & F9 & R11;
@@ -645,12 +662,11 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5),
                            c4 = ~(T3 | T4 | T5 | T6);
             const uint32_t b0 = c1 | c3, b1 = c2 | c3;
-            const int mi0 = 12 * 32 * w + rho;
             while (any) {
                 const int bit = __ffs(any) - 1;
                 any &= any - 1;
                 const uint32_t cs = ((b0 >> bit) & 1u) | (((b1 >> bit) & 1u) << 1) | (((c4 >> bit) & 1u) << 2);
-                const int mi = mi0 + 12 * bit;
+                const int mi = 32 * w + bit;
                 const uint32_t qi = atomicAdd(&s_qn[cs], 1u);
                 if (qi < (uint32_t)kQueueCap)
                     queue[cs * kQueueCap + qi] = (uint16_t)mi;
@@ -754,19 +770,16 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             // demod_2400.rs:158-160: P0 = 5*(mi+19) + try_phase, try_phase = 4+tt
             const int A = jl + kHaloFront + 19;
             const int qA = A / 12, rA = A - 12 * qA;
-            const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
             uint32_t f[5];
 #pragma unroll
             for (int r = 0; r < 5; r++) {
-                const int z = phi0 + 12 * r;            // P_r = 5*(A+e5) + z
-                const int zd = (z * 205) >> 10;         // z / 5 for z < 64
-                const int phi = z - 5 * zd;
-                int rho = rA + e5 + zd, q = qA;         // sample A+e5+zd = 12q + rho
+                const uint32_t e = s_lut[5 * tt + r];
+                int rho = rA + (int)(e & 0xffu), q = qA;   // sample A+delta = 12q + rho
                 if (rho >= 12) {
                     rho -= 12;
                     q++;
                 }
-                const uint32_t *st = planes + (phi * 12 + rho) * WP + (q >> 5);
+                const uint32_t *st = planes + (e >> 8) + rho * WP + (q >> 5);
                 f[r] = __funnelshift_r(st[0], st[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
             }
             if (tt == 0)
