@@ -88,7 +88,7 @@ __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b *
 
 // shared memory plan of the scan kernel for tile size T
 struct ScanSmem {
-    int steps, MP, MPc, WP, nw, dd_words;
+    int steps, MP, MPc, WP, nw, dd_words, edge_bytes;
     size_t off_dd, off_planes, off_edges, off_surv, off_tabs, off_queue, off_cand, bytes;
     __host__ __device__ explicit ScanSmem(int T)
     {
@@ -107,8 +107,10 @@ struct ScanSmem {
         off_planes = o;                               // S[phi][rho][word], de-interleaved mod 12
         o += (size_t)5 * 12 * WP * 4;
         off_edges = o;                                // R then F: one bit per sample, consecutive
-        o += (size_t)2 * (MPc / 8 + 16);
+        edge_bytes = round_up(MPc / 8 + 16, 16);
         o = (o + 15) & ~(size_t)15;
+        off_edges = o;
+        o += (size_t)2 * edge_bytes;
         off_surv = o;
         o += (size_t)nw * 4;
         off_tabs = o;
@@ -490,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd is dead)
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [5][12][WP]
     uint8_t *Rc = smem + L.off_edges;                 // rising-edge bit of every sample (bit i <-> m[i] < m[i+1])
-    uint8_t *Fc = Rc + (L.MPc / 8 + 16);              // falling-edge bit
+    uint8_t *Fc = Rc + L.edge_bytes;                  // falling-edge bit
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);     // [5][kQueueCap]
