@@ -39,11 +39,13 @@ constexpr int kHaloTot = 296;    // mags needed per tile = T + 296 (max tap j+28
 constexpr int kStep = 384;       // 12 residues x 32 lanes: samples per warp step
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 248;      // new samples per warp iteration of P1 (8 per lane, lane 31 overlaps)
-constexpr int kDDBlock = 396;    // 384 first differences + 12 mirrored from the next block
+constexpr int kChunk = 248;      // new pair-slots per warp iteration of P1 (8 per lane, lane 31 overlaps)
+constexpr int kHalf = 192;       // half block: 12 residues x 16 lanes-steps
+constexpr int kHalfPad = 204;    // 192 pair-slots + 12 mirrored from the next half block
 constexpr int kQueueCap = 512;   // template matches per template case awaiting the gates (overflow: in place)
 constexpr int kCandCap = 352;    // survivors decoded per window
 constexpr int kFieldItems = 5 * kCandCap;   // (survivor, try_phase) items whose fields are staged
+constexpr int kLutWords = 12 * 25;          // field-extraction table: (residue of j+19, try_phase, field)
 constexpr int kMaxTile = 8184;   // tile mag indices (< T+2) fit 13 bits; surv words <= 256
 constexpr int kDefaultTile = 7768;   // 21 blocks of 384: 252 (block, residue) items per 256 threads
 constexpr int kTabWords = 256 + 256 + 64 + 256 + 8;   // CRC-24 field tables (see build_crc_tabs)
@@ -86,35 +88,39 @@ struct ScanParams {
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
-// shared memory plan of the scan kernel for tile size T
+// shared memory plan of the scan kernel for tile size T.
+// The halo-extended tile is H blocks of 384 samples = 2H half blocks of 192; the first H half
+// blocks form stream A, the last H stream B, and everything downstream of the magnitude works
+// on (A, B) sample pairs in the packed f32x2 pipe.
 struct ScanSmem {
     int steps, MP, MPc, WP, nw, dd_words, edge_bytes;
-    size_t off_dd, off_planes, off_edges, off_surv, off_tabs, off_queue, off_cand, bytes;
+    size_t off_dd, off_planes, off_edges, off_surv, off_tabs, off_queue, off_cand, off_lut, bytes;
     __host__ __device__ explicit ScanSmem(int T)
     {
-        steps = (T + kHaloTot + kStep - 1) / kStep;   // 384-sample blocks (12 residues x 32)
+        steps = (T + kHaloTot + kStep - 1) / kStep;   // H: 384-sample blocks
         MP = steps * kStep;
-        MPc = round_up(MP + 16, kChunk) + 8;          // P1 works in 248-sample warp chunks (+ lane 31)
+        MPc = MP + 64;                                // u16 magnitudes incl. the extra pair-slots
         WP = steps + 1;
         nw = (T + 31) / 32;
-        size_t o = (size_t)(MPc + 8) * 2;             // u16 magnitudes
+        size_t o = (size_t)(MPc + 8) * 2;
         o = (o + 15) & ~(size_t)15;
-        off_dd = o;                                   // i32 first differences, 396 per block;
-        dd_words = kDDBlock * ((MPc + kStep - 1) / kStep + 1);
+        off_dd = o;                                   // float2 first differences, 204 pair-slots per half block
+        dd_words = 2 * kHalfPad * (steps + 1);
         if (dd_words < kFieldItems * 5)               // later reused as the P4 field buffer
             dd_words = kFieldItems * 5;
         o += (size_t)dd_words * 4;
         off_planes = o;                               // S[phi][rho][word], de-interleaved mod 12
         o += (size_t)5 * 12 * WP * 4;
-        off_edges = o;                                // R then F: one bit per sample, consecutive
         edge_bytes = round_up(MPc / 8 + 16, 16);
         o = (o + 15) & ~(size_t)15;
-        off_edges = o;
+        off_edges = o;                                // R then F: one bit per sample, consecutive
         o += (size_t)2 * edge_bytes;
         off_surv = o;
         o += (size_t)nw * 4;
         off_tabs = o;
         o += (size_t)kTabWords * 4;
+        off_lut = o;
+        o += (size_t)kLutWords * 4;
         off_queue = o;
         o += (size_t)5 * kQueueCap * 2;
         off_cand = o;
@@ -184,13 +190,19 @@ __device__ __forceinline__ u64x f2_add(u64x a, u64x b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+__device__ __forceinline__ u64x f2_sub(u64x a, u64x b)
+{
+    u64x r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
 __device__ __forceinline__ u64x f2_add_rz(u64x a, u64x b)
 {
     u64x r;
     asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
-__device__ __forceinline__ void mag_bits_fast2(uint32_t wa, uint32_t wb, uint32_t &ra, uint32_t &rb)
+__device__ __forceinline__ u64x mag_pair_fast2(uint32_t wa, uint32_t wb)
 {
     const uint32_t ta = wa ^ 0x80008000u, tb = wb ^ 0x80008000u;
     const u64x fre = f2_pack(__uint_as_float(__byte_perm(ta, 0x4B000000u, 0x7610)),
@@ -212,18 +224,13 @@ __device__ __forceinline__ void mag_bits_fast2(uint32_t wa, uint32_t wb, uint32_
     const u64x s = f2_fma(eh, y, s0);                           // s0 + (x - s0^2) * y/2
     float va, vb;
     f2_unpack(f2_fma(s, f2_pack(65535.0f, 65535.0f), f2_pack(0.5f, 0.5f)), va, vb);
-    const u64x r = f2_add_rz(f2_pack(fminf(va, 65535.0f), fminf(vb, 65535.0f)),
-                             f2_pack(8388608.0f, 8388608.0f));
-    float fa, fb;
-    f2_unpack(r, fa, fb);
-    ra = __float_as_uint(fa);
-    rb = __float_as_uint(fb);
+    return f2_add_rz(f2_pack(fminf(va, 65535.0f), fminf(vb, 65535.0f)), f2_pack(8388608.0f, 8388608.0f));
 }
 __device__ __forceinline__ uint32_t mag_bits_fast(uint32_t w)
 {
-    uint32_t a, b;
-    mag_bits_fast2(w, w, a, b);
-    return a;
+    float a, b;
+    f2_unpack(mag_pair_fast2(w, w), a, b);
+    return __float_as_uint(a);
 }
 
 // ------------------------------------------------------------------ CRC-24 by fields
@@ -488,8 +495,9 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     extern __shared__ __align__(16) unsigned char smem[];
     const ScanSmem L(p.T);
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
-    int *dd = reinterpret_cast<int *>(smem + L.off_dd);
-    uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd is dead)
+    u64x *dd2 = reinterpret_cast<u64x *>(smem + L.off_dd);                  // (A, B) first-difference pairs
+    uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd2 is dead)
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.off_lut);         // [12][5][5] field extraction table
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [5][12][WP]
     uint8_t *Rc = smem + L.off_edges;                 // rising-edge bit of every sample (bit i <-> m[i] < m[i+1])
     uint8_t *Fc = Rc + L.edge_bytes;                  // falling-edge bit
@@ -498,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);     // [5][kQueueCap]
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
     __shared__ uint32_t s_warp_tot[kWarps];
-    __shared__ uint32_t s_base, s_count, s_ok, s_qn[5], s_nlong, s_nshort, s_lut[25];
+    __shared__ uint32_t s_base, s_count, s_ok, s_qn[5], s_nlong, s_nshort;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -513,71 +521,95 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     }
     const int npos = min(p.T, len - tile_start);
     const int steps = (npos + kHaloTot + kStep - 1) / kStep;   // 384-blocks actually needed
-    const int MPe = steps * kStep;
     const int WP = L.WP;
 
-    // ---- P1: magnitudes m[0, MPe+8) (u16) and differences d[0, MPe+12) (i32) -> shared memory.
-    // A warp takes 248 new samples per iteration, 8 per lane; lane 31 recomputes the next
-    // chunk's first 8 only to hand lane 30 its right neighbour.
+    // ---- P1: magnitudes (u16), edge bits and first differences -> shared memory.
+    // Pair-slot s holds sample s of stream A (tile samples [0, 192H)) and sample 192H+s of
+    // stream B.  A warp takes 248 new pair-slots per iteration, 8 per lane (2 x 2 LDG.128);
+    // lane 31 recomputes the next chunk's first 8 only to hand lane 30 its right neighbour.
+    const int H = steps;
+    const int offB = kHalf * H;
     {
-        const int nchunk = (MPe + 16 + kChunk - 1) / kChunk;
+        const int nslots = kHalf * H + 16;      // + the right neighbours / pad mirror of the last half block
+        const int nchunk = (nslots + kChunk - 1) / kChunk;
         const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of m[0]
         const int i0 = tile_start - kHaloFront;                  // data index of m[0]
         const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
         const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
-        uint32_t wn[8];
-        if (!FROM_MAG && warp < nchunk)
-            load_iq8(b32, s0 + warp * kChunk + 8 * lane, len, p.vec_ok, wn);
+        uint32_t wan[8], wbn[8];
+        if (!FROM_MAG && warp < nchunk) {
+            load_iq8(b32, s0 + warp * kChunk + 8 * lane, len, p.vec_ok, wan);
+            load_iq8(b32, s0 + offB + warp * kChunk + 8 * lane, len, p.vec_ok, wbn);
+        }
         for (int ch = warp; ch < nchunk; ch += kWarps) {
-            const int mi = ch * kChunk + 8 * lane;
-            uint32_t r[9];   // 0x4B000000 + magnitude
+            const int sl = ch * kChunk + 8 * lane;
+            u64x r[9];   // (A, B) pairs of f32 bit patterns 0x4B000000 + magnitude = 2^23 + magnitude
             if (!FROM_MAG) {
-                uint32_t w[8];
 #pragma unroll
                 for (int e = 0; e < 8; e++)
-                    w[e] = wn[e];
-                if (ch + kWarps < nchunk)   // next chunk's loads fly while this one computes
-                    load_iq8(b32, s0 + (ch + kWarps) * kChunk + 8 * lane, len, p.vec_ok, wn);
-                mag_bits_fast2(w[0], w[1], r[0], r[1]);
-                mag_bits_fast2(w[2], w[3], r[2], r[3]);
-                mag_bits_fast2(w[4], w[5], r[4], r[5]);
-                mag_bits_fast2(w[6], w[7], r[6], r[7]);
+                    r[e] = mag_pair_fast2(wan[e], wbn[e]);
+                if (ch + kWarps < nchunk) {   // next chunk's loads fly while the stores below drain
+                    load_iq8(b32, s0 + (ch + kWarps) * kChunk + 8 * lane, len, p.vec_ok, wan);
+                    load_iq8(b32, s0 + offB + (ch + kWarps) * kChunk + 8 * lane, len, p.vec_ok, wbn);
+                }
             } else {
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
-                    const int idx = i0 + mi + e;
-                    r[e] = 0x4B000000u + ((idx >= 0 && idx < kMagLen) ? (uint32_t)__ldg(d16 + idx) : 0u);
+                    const int ia = i0 + sl + e, ib = ia + offB;
+                    const uint32_t ma = (ia >= 0 && ia < kMagLen) ? (uint32_t)__ldg(d16 + ia) : 0u;
+                    const uint32_t mb = (ib >= 0 && ib < kMagLen) ? (uint32_t)__ldg(d16 + ib) : 0u;
+                    r[e] = f2_pack(__uint_as_float(0x4B000000u + ma), __uint_as_float(0x4B000000u + mb));
                 }
             }
             r[8] = __shfl_down_sync(0xffffffffu, r[0], 1);
-            if (lane < 31) {
-                // u16 magnitudes, 8 per lane
-                *reinterpret_cast<uint4 *>(mag + mi) =
-                    make_uint4(__byte_perm(r[0], r[1], 0x5410), __byte_perm(r[2], r[3], 0x5410),
-                               __byte_perm(r[4], r[5], 0x5410), __byte_perm(r[6], r[7], 0x5410));
-                // first differences (the bit patterns share a binade: they subtract like integers)
-                int dv[8];
+            if (lane < 31 && sl < nslots) {
+                uint32_t ra[8], rb[8];
+                uint32_t fA = 0, fB = 0, rA_ = 0, rB_ = 0;
+                u64x dv[8];
 #pragma unroll
-                for (int e = 0; e < 8; e++)
-                    dv[e] = (int)(r[e + 1] - r[e]);
-                // edge bits of these 8 samples (demod_2400.rs:221-317 compares neighbours only)
-                uint32_t fbits = 0, rbits = 0;
+                for (int e = 0; e < 8; e++) {
+                    float x, y;
+                    f2_unpack(r[e], x, y);
+                    ra[e] = __float_as_uint(x);
+                    rb[e] = __float_as_uint(y);
+                    dv[e] = f2_sub(r[e + 1], r[e]);      // m[i+1]-m[i], exact
+                }
+                // edge bits of these samples (demod_2400.rs:221-317 compares neighbours only)
 #pragma unroll
                 for (int e = 7; e >= 0; e--) {
-                    fbits = __funnelshift_l((uint32_t)dv[e], fbits, 1);      // m[i+1]-m[i] < 0: falling
-                    rbits = __funnelshift_l((uint32_t)(-dv[e]), rbits, 1);   // rising
+                    float x, y, nx, ny;
+                    f2_unpack(dv[e], x, y);
+                    f2_unpack(f2_sub(r[e], r[e + 1]), nx, ny);
+                    fA = __funnelshift_l(__float_as_uint(x), fA, 1);     // m[i+1]-m[i] < 0: falling
+                    fB = __funnelshift_l(__float_as_uint(y), fB, 1);
+                    rA_ = __funnelshift_l(__float_as_uint(nx), rA_, 1);  // rising
+                    rB_ = __funnelshift_l(__float_as_uint(ny), rB_, 1);
                 }
-                Fc[mi >> 3] = (uint8_t)fbits;
-                Rc[mi >> 3] = (uint8_t)rbits;
-                const int blk = mi / kStep, off = mi - blk * kStep;
-                int *dst = dd + kDDBlock * blk + off;
-                *reinterpret_cast<int4 *>(dst) = make_int4(dv[0], dv[1], dv[2], dv[3]);
-                *reinterpret_cast<int4 *>(dst + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
-                if (off < 12 && blk > 0) {   // mirror into the previous block's pad
-                    int *pad = dd + kDDBlock * (blk - 1) + kStep + off;
-                    *reinterpret_cast<int4 *>(pad) = make_int4(dv[0], dv[1], dv[2], dv[3]);
-                    if (off == 0)
-                        *reinterpret_cast<int4 *>(pad + 4) = make_int4(dv[4], dv[5], dv[6], dv[7]);
+                if (sl < offB) {   // the extra pair-slots duplicate stream B's first samples
+                    *reinterpret_cast<uint4 *>(mag + sl) =
+                        make_uint4(__byte_perm(ra[0], ra[1], 0x5410), __byte_perm(ra[2], ra[3], 0x5410),
+                                   __byte_perm(ra[4], ra[5], 0x5410), __byte_perm(ra[6], ra[7], 0x5410));
+                    Fc[sl >> 3] = (uint8_t)fA;
+                    Rc[sl >> 3] = (uint8_t)rA_;
+                }
+                *reinterpret_cast<uint4 *>(mag + offB + sl) =
+                    make_uint4(__byte_perm(rb[0], rb[1], 0x5410), __byte_perm(rb[2], rb[3], 0x5410),
+                               __byte_perm(rb[4], rb[5], 0x5410), __byte_perm(rb[6], rb[7], 0x5410));
+                Fc[(offB + sl) >> 3] = (uint8_t)fB;
+                Rc[(offB + sl) >> 3] = (uint8_t)rB_;
+                const int hb = sl / kHalf, off = sl - hb * kHalf;
+                u64x *dst = dd2 + kHalfPad * hb + off;
+#pragma unroll
+                for (int e = 0; e < 8; e += 2)
+                    *reinterpret_cast<ulonglong2 *>(dst + e) = make_ulonglong2(dv[e], dv[e + 1]);
+                if (off < 12 && hb > 0) {   // mirror into the previous half block's pad
+                    u64x *pad = dd2 + kHalfPad * (hb - 1) + kHalf + off;
+                    *reinterpret_cast<ulonglong2 *>(pad) = make_ulonglong2(dv[0], dv[1]);
+                    *reinterpret_cast<ulonglong2 *>(pad + 2) = make_ulonglong2(dv[2], dv[3]);
+                    if (off == 0) {
+                        *reinterpret_cast<ulonglong2 *>(pad + 4) = make_ulonglong2(dv[4], dv[5]);
+                        *reinterpret_cast<ulonglong2 *>(pad + 6) = make_ulonglong2(dv[6], dv[7]);
+                    }
                 }
             }
         }
@@ -590,43 +622,64 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
         planes[c * WP + steps] = 0;   // pad word read by funnel shifts
     if (tid < 5)
         s_qn[tid] = 0;
-    if (tid < 25) {
-        // field r of try-phase 4+tt starts at 1/5-sample position 5*(A+e5)+z (A = j+19):
-        // sample offset delta from A and plane base of its correlator phi
-        const int tt = tid / 5, r = tid - 5 * tt;
+    for (int c = tid; c < kLutWords; c += kThreads) {
+        // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
+        // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream, and whether
+        // the stream index q = A/12 advances by one
+        const int ra = c / 25, tt = (c - 25 * ra) / 5, r = c - 25 * ra - 5 * tt;
         const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
         const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
-        s_lut[tid] = (uint32_t)(e5 + zd) | ((uint32_t)(phi * 12 * WP) << 8);
+        const int rr = ra + e5 + zd, wrap = rr >= 12 ? 1 : 0;
+        lut[c] = (uint32_t)((phi * 12 + rr - 12 * wrap) * WP) | ((uint32_t)wrap << 16);
     }
     __syncthreads();
 
-    // ---- P2: bit planes.  One lane = one residue class rho of one 384-block: 32 samples at
-    // stride 12, each contributing one bit to the five correlator-sign planes S[phi] and to
-    // the edge planes R (rising), F (falling); bits are shifted in with funnel shifts.
+    // ---- P2: correlator sign planes.  One lane = one residue class rho of half block hb of
+    // stream A and of stream B (hb + H): 16 samples at stride 12 of each, processed as (A, B)
+    // pairs in the packed f32x2 pipe; sign bits are shifted in with funnel shifts.
     // demod_2400.rs:72-83 on negated first differences u,v,w (so that "x > 0" is a sign bit):
     //   -[5,-3,-2] = 5u+2v   -[4,-1,-3] = 4u+3v   -[3,1,-4] = 3u+4v   -[2,3,-5] = 2u+5v
-    //   -[1,5,-5,-1] = u+6v+w
-    for (int item = tid; item < 12 * steps; item += kThreads) {
-        const int blk = item / 12, rho = item - 12 * blk;
-        const int *dp = dd + kDDBlock * blk + rho;
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    //   -[1,5,-5,-1] = u+6v+w      (all exact in f32: |.| < 2^20)
+    {
+        const u64x five = f2_pack(5.0f, 5.0f);
+        uint16_t *ph = reinterpret_cast<uint16_t *>(planes);
+        for (int task = tid; task < 12 * H; task += kThreads) {
+            const int hb = task / 12, rho = task - 12 * hb;
+            const u64x *dp = dd2 + kHalfPad * hb + rho;
+            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;
 #pragma unroll
-        for (int q = 31; q >= 0; q--) {
-            const int u = dp[12 * q], v = dp[12 * q + 1], w = dp[12 * q + 2];
-            const int g = v - u;
-            const int x0 = 5 * u + 2 * v, x1 = x0 + g, x2 = x1 + g, x3 = x2 + g, x4 = x3 + g + w;
-            a0 = __funnelshift_l((uint32_t)x0, a0, 1);
-            a1 = __funnelshift_l((uint32_t)x1, a1, 1);
-            a2 = __funnelshift_l((uint32_t)x2, a2, 1);
-            a3 = __funnelshift_l((uint32_t)x3, a3, 1);
-            a4 = __funnelshift_l((uint32_t)x4, a4, 1);
+            for (int q = 15; q >= 0; q--) {
+                const u64x u = dp[12 * q], v = dp[12 * q + 1], w = dp[12 * q + 2];
+                const u64x g = f2_sub(v, u);
+                const u64x x0 = f2_fma(u, five, f2_add(v, v));
+                const u64x x1 = f2_add(x0, g), x2 = f2_add(x1, g), x3 = f2_add(x2, g);
+                const u64x x4 = f2_add(f2_add(x3, g), w);
+                float lo, hi;
+                f2_unpack(x0, lo, hi);
+                a0 = __funnelshift_l(__float_as_uint(lo), a0, 1);
+                b0 = __funnelshift_l(__float_as_uint(hi), b0, 1);
+                f2_unpack(x1, lo, hi);
+                a1 = __funnelshift_l(__float_as_uint(lo), a1, 1);
+                b1 = __funnelshift_l(__float_as_uint(hi), b1, 1);
+                f2_unpack(x2, lo, hi);
+                a2 = __funnelshift_l(__float_as_uint(lo), a2, 1);
+                b2 = __funnelshift_l(__float_as_uint(hi), b2, 1);
+                f2_unpack(x3, lo, hi);
+                a3 = __funnelshift_l(__float_as_uint(lo), a3, 1);
+                b3 = __funnelshift_l(__float_as_uint(hi), b3, 1);
+                f2_unpack(x4, lo, hi);
+                a4 = __funnelshift_l(__float_as_uint(lo), a4, 1);
+                b4 = __funnelshift_l(__float_as_uint(hi), b4, 1);
+            }
+            // stream bit q = 16*hb + step: 16 bits per half block
+            uint16_t *pa = ph + 2 * (rho * WP) + hb, *pb = pa + H;
+            const int ps = 2 * 12 * WP;
+            pa[0 * ps] = (uint16_t)a0; pb[0 * ps] = (uint16_t)b0;
+            pa[1 * ps] = (uint16_t)a1; pb[1 * ps] = (uint16_t)b1;
+            pa[2 * ps] = (uint16_t)a2; pb[2 * ps] = (uint16_t)b2;
+            pa[3 * ps] = (uint16_t)a3; pb[3 * ps] = (uint16_t)b3;
+            pa[4 * ps] = (uint16_t)a4; pb[4 * ps] = (uint16_t)b4;
         }
-        uint32_t *pl = planes + rho * WP + blk;
-        pl[0 * 12 * WP] = a0;
-        pl[1 * 12 * WP] = a1;
-        pl[2 * 12 * WP] = a2;
-        pl[3 * 12 * WP] = a3;
-        pl[4 * 12 * WP] = a4;
     }
     __syncthreads();
 
@@ -772,16 +825,13 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             // demod_2400.rs:158-160: P0 = 5*(mi+19) + try_phase, try_phase = 4+tt
             const int A = jl + kHaloFront + 19;
             const int qA = A / 12, rA = A - 12 * qA;
+            const uint32_t *lrow = lut + 25 * rA + 5 * tt;
             uint32_t f[5];
 #pragma unroll
             for (int r = 0; r < 5; r++) {
-                const uint32_t e = s_lut[5 * tt + r];
-                int rho = rA + (int)(e & 0xffu), q = qA;   // sample A+delta = 12q + rho
-                if (rho >= 12) {
-                    rho -= 12;
-                    q++;
-                }
-                const uint32_t *st = planes + (e >> 8) + rho * WP + (q >> 5);
+                const uint32_t e = lrow[r];
+                const int q = qA + (int)(e >> 16);
+                const uint32_t *st = planes + (e & 0xffffu) + (q >> 5);
                 f[r] = __funnelshift_r(st[0], st[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
             }
             if (tt == 0)
