@@ -222,23 +222,28 @@ def main() -> int:
 
     # ---- roofline of the dominant kernel (scan): algorithmic bytes = 4 B per IQ sample
     peak, peak_src = peaks()
-    scan_ms = tim["scan_ms"] / max(tim["scan_launches"], 1)
-    alg_bytes = 4.0 * nb * SAMPLES
-    achieved = alg_bytes / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    # (the scan kernel is launched once per chunk of tiles; sum over the timed region)
+    scan_launches = max(tim["scan_launches"], 1)
+    scan_ms = tim["scan_ms"] / scan_launches
+    alg_bytes = 4.0 * tim["samples"] / scan_launches
+    achieved = 4.0 * tim["samples"] / (tim["scan_ms"] * 1e-3) / 1e9 if tim["scan_ms"] > 0 else 0.0
     traffic = None
     try:
         with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
             tj = json.load(f)
             traffic = tj.get("dram_bytes_per_sample", None)
             if traffic is not None:
-                traffic = traffic * nb * SAMPLES
+                traffic = traffic * tim["samples"] / scan_launches
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
                 "kernel": "scan_kernel<false>", "kernel_ms_per_launch": scan_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "kernel_share_of_step": (tim["scan_ms"] / ms) if ms else None}
+                "kernel_share_of_step": (tim["scan_ms"] / ms) if ms else None,
+                "kernel_ms_per_step": tim["scan_ms"] / args.steps,
+                "decode_kernel_ms_per_step": tim["decode_ms"] / args.steps,
+                "resolve_kernels_ms_per_step": tim["resolve_ms"] / args.steps}
 
     # ---- e2e: host-buffer C-ABI call, H2D + D2H inside the timed region
     e2e = None

@@ -11,8 +11,8 @@ python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_$TAG.json"))
 r = d["roofline"]
-print("value %.0f Msps  step %.3f ms  scan %.3f ms  frac %.4f  e2e %.0f  cpu %.1f parity %s launches %d" % (
-    d["value"], d["ms_per_step"], r["kernel_ms_per_launch"], r["frac"], (d["e2e"] or {}).get("value", 0),
+print("value %.0f Msps  step %.3f ms  scan %.3f ms decode %.3f ms resolve %.3f ms  frac %.4f  e2e %.0f  cpu %.1f parity %s launches %d" % (
+    d["value"], d["ms_per_step"], r["kernel_ms_per_step"], r["decode_kernel_ms_per_step"], r["resolve_kernels_ms_per_step"], r["frac"], (d["e2e"] or {}).get("value", 0),
     (d["cpu_baseline"] or {}).get("value", 0), (d["cpu_baseline"] or {}).get("parity_on_sample"), d["gpu_launches"]))
 PY
 tail -3 gpurun_out/bench_$TAG.err
