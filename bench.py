@@ -242,7 +242,7 @@ def main() -> int:
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": (tim["scan_ms"] / ms) if ms else None,
                 "kernel_ms_per_step": tim["scan_ms"] / args.steps,
-                "decode_kernel_ms_per_step": tim["decode_ms"] / args.steps,
+                "decode_kernel_ms_per_step": tim.get("decode_ms", 0.0) / args.steps,
                 "resolve_kernels_ms_per_step": tim["resolve_ms"] / args.steps}
 
     # ---- e2e: host-buffer C-ABI call, H2D + D2H inside the timed region

@@ -49,7 +49,7 @@ class Timing(C.Structure):
     _fields_ = [
         ("scan_ms", C.c_double), ("resolve_ms", C.c_double), ("h2d_ms", C.c_double),
         ("d2h_ms", C.c_double), ("scan_launches", C.c_uint64), ("other_launches", C.c_uint64),
-        ("samples", C.c_uint64), ("candidates", C.c_uint64), ("decode_ms", C.c_double),
+        ("samples", C.c_uint64), ("candidates", C.c_uint64),
     ]
 
 

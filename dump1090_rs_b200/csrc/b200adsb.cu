@@ -42,11 +42,7 @@ struct Pending {
 
 struct b200adsb_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, decode_stream = nullptr;
-    cudaEvent_t ev_scan[2] = {nullptr, nullptr}, ev_dec[2] = {nullptr, nullptr};
-    uint32_t *d_hand = nullptr;          // scan -> decode hand-off ring (two halves)
-    size_t hand_words_cap = 0;
-    uint64_t chunk_seq = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
     bool own_stream = false;
     int tile_opt = 0, pool_shift = 5, profile = 0, h2d_chunk = 64;
 
@@ -75,7 +71,7 @@ struct b200adsb_ctx {
 
     unsigned long long next_ordinal = 0;   // stream position (buffers) for the fused entry points
     Pending cur;
-    std::vector<EventPair> scan_events, other_events, decode_events;
+    std::vector<EventPair> scan_events, other_events;
     std::vector<cudaEvent_t> chunk_events;
     b200adsb_timing timing{};
     char err[256] = {0};
@@ -210,21 +206,21 @@ int pick_tile(const b200adsb_ctx *c, size_t n_buffers, size_t spb)
     return 472;
 }
 
-void prof_begin(b200adsb_ctx *c, std::vector<EventPair> &v, cudaStream_t st = nullptr)
+void prof_begin(b200adsb_ctx *c, std::vector<EventPair> &v)
 {
     if (!c->profile)
         return;
     EventPair p;
     cudaEventCreate(&p.a);
     cudaEventCreate(&p.b);
-    cudaEventRecord(p.a, st ? st : c->stream);
+    cudaEventRecord(p.a, c->stream);
     v.push_back(p);
 }
-void prof_end(b200adsb_ctx *c, std::vector<EventPair> &v, cudaStream_t st = nullptr)
+void prof_end(b200adsb_ctx *c, std::vector<EventPair> &v)
 {
     if (!c->profile)
         return;
-    cudaEventRecord(v.back().b, st ? st : c->stream);
+    cudaEventRecord(v.back().b, c->stream);
 }
 void prof_collect(b200adsb_ctx *c)   // after a stream sync
 {
@@ -242,16 +238,8 @@ void prof_collect(b200adsb_ctx *c)   // after a stream sync
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
     }
-    for (auto &p : c->decode_events) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
-            c->timing.decode_ms += ms;
-        cudaEventDestroy(p.a);
-        cudaEventDestroy(p.b);
-    }
     c->scan_events.clear();
     c->other_events.clear();
-    c->decode_events.clear();
 }
 
 int read_counters(b200adsb_ctx *c)
@@ -262,22 +250,17 @@ int read_counters(b200adsb_ctx *c)
     return B200ADSB_OK;
 }
 
-// Stage 1 over buffers [b0, b0+nb) of the pending batch: scan_kernel (magnitude, edge bits,
-// correlator sign planes, preamble gate) on the main stream and decode_kernel (field
-// extraction, CRC-24, classification) on the decode stream, chunk by chunk through a
-// double-buffered hand-off ring small enough to stay in L2.
-constexpr uint32_t kChunkTiles = 148 * 16;
-
+// launch the scan kernel over buffers [b0, b0+nb) of the pending batch
 int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
 {
     const Pending &q = c->cur;
-    const uint32_t t_begin = b0 * (uint32_t)q.tpb, t_end = (b0 + nb) * (uint32_t)q.tpb;
-    if (t_end == t_begin)
-        return B200ADSB_OK;
     ScanParams p{};
-    p.in = q.in;
-    p.lengths = q.lengths;
-    p.n_buffers = q.n_buffers;
+    if (q.from_mag)
+        p.in = reinterpret_cast<const uint16_t *>(q.in) + (size_t)b0 * q.stride;
+    else
+        p.in = reinterpret_cast<const int16_t *>(q.in) + 2 * (size_t)b0 * q.stride;
+    p.lengths = q.lengths ? q.lengths + b0 : nullptr;
+    p.n_buffers = nb;
     p.spb = q.spb;
     p.stride = q.stride;
     p.T = q.T;
@@ -285,62 +268,32 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.vec_ok = (!q.from_mag && ((uintptr_t)q.in % 16 == 0) && (q.stride % 4 == 0)) ? 1 : 0;
     p.rec = c->d_rec;
     p.pool_cap = (uint32_t)std::min<size_t>(c->pool_cap, 0xffffffffu);
-    p.tile_dir = c->d_tile_dir;
+    p.tile_dir = c->d_tile_dir + (size_t)b0 * q.tpb;
     p.counters = c->d_counters;
     p.ev_keys = c->d_ev_keys;
     p.ev_ord = c->d_ev_ord;
     p.ev_used = c->d_ev_used;
     p.ev_mask = kEvSlots - 1;
-    p.ord_first = q.ord_first;
+    p.ord_first = q.ord_first + (unsigned long long)b0 * q.ord_stride;
     p.ord_stride = q.ord_stride;
     p.crc_tabs = c->d_crc_tabs;
     const ScanSmem L(q.T);
-    const DecodeSmem D(q.T);
-    const size_t hw = (size_t)L.hand_words();
-    const size_t need = 2 * (size_t)kChunkTiles * hw;
-    if (need > c->hand_words_cap) {
-        int rc = grow(c, &c->d_hand, &c->hand_words_cap, need);
-        if (rc) return rc;
-    }
-    p.hand = c->d_hand;
+    const uint32_t grid = nb * (uint32_t)q.tpb;
+    if (grid == 0)
+        return B200ADSB_OK;
+    prof_begin(c, c->scan_events);
     if (q.from_mag) {
         CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
         CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        scan_kernel<true><<<grid, kThreads, L.bytes, c->stream>>>(p);
     } else {
         CK(c, cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
         CK(c, cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        scan_kernel<false><<<grid, kThreads, L.bytes, c->stream>>>(p);
     }
-    CK(c, cudaFuncSetAttribute(decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.bytes));
-    CK(c, cudaFuncSetAttribute(decode_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    uint32_t launched = 0;
-    for (uint32_t t0 = t_begin; t0 < t_end; t0 += kChunkTiles, launched++) {
-        const uint32_t n = std::min(kChunkTiles, t_end - t0);
-        const int slot = (int)(c->chunk_seq & 1);
-        if (c->chunk_seq >= 2)   // the decode of the chunk that used this half of the ring is done
-            CK(c, cudaStreamWaitEvent(c->stream, c->ev_dec[slot], 0));
-        p.tile0 = t0;
-        p.hand_slot0 = (uint32_t)slot * kChunkTiles;
-        prof_begin(c, c->scan_events);
-        if (q.from_mag)
-            scan_kernel<true><<<n, kThreads, L.bytes, c->stream>>>(p);
-        else
-            scan_kernel<false><<<n, kThreads, L.bytes, c->stream>>>(p);
-        prof_end(c, c->scan_events);
-        CK(c, cudaGetLastError());
-        CK(c, cudaEventRecord(c->ev_scan[slot], c->stream));
-        CK(c, cudaStreamWaitEvent(c->decode_stream, c->ev_scan[slot], 0));
-        prof_begin(c, c->decode_events, c->decode_stream);
-        decode_kernel<<<n, kThreads, D.bytes, c->decode_stream>>>(p);
-        prof_end(c, c->decode_events, c->decode_stream);
-        CK(c, cudaGetLastError());
-        CK(c, cudaEventRecord(c->ev_dec[slot], c->decode_stream));
-        c->chunk_seq++;
-        c->timing.scan_launches++;
-        c->timing.other_launches++;
-    }
-    // everything later on the main stream (counters read-back, resolve) follows the decodes
-    CK(c, cudaStreamWaitEvent(c->stream, c->ev_dec[0], 0));
-    CK(c, cudaStreamWaitEvent(c->stream, c->ev_dec[1], 0));
+    prof_end(c, c->scan_events);
+    CK(c, cudaGetLastError());
+    c->timing.scan_launches++;
     c->timing.samples += (uint64_t)nb * q.spb;
     return B200ADSB_OK;
 }
@@ -580,12 +533,6 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
         c->own_stream = true;
     }
     CKC(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    CKC(cudaStreamCreateWithFlags(&c->decode_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        CKC(cudaEventCreateWithFlags(&c->ev_scan[i], cudaEventDisableTiming));
-        CKC(cudaEventCreateWithFlags(&c->ev_dec[i], cudaEventDisableTiming));
-        CKC(cudaEventRecord(c->ev_dec[i], c->decode_stream));
-    }
     CKC(cudaMalloc((void **)&c->d_counters, C_WORDS * 4));
     CKC(cudaMemset(c->d_counters, 0, C_WORDS * 4));
     CKC(cudaMallocHost((void **)&c->h_counters, C_WORDS * 4));
@@ -642,15 +589,6 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_frames);
     cudaFree(c->d_counts);
     cudaFree(c->d_lengths);
-    if (c->decode_stream) {
-        cudaStreamSynchronize(c->decode_stream);
-        cudaStreamDestroy(c->decode_stream);
-    }
-    for (int i = 0; i < 2; i++) {
-        if (c->ev_scan[i]) cudaEventDestroy(c->ev_scan[i]);
-        if (c->ev_dec[i]) cudaEventDestroy(c->ev_dec[i]);
-    }
-    cudaFree(c->d_hand);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;

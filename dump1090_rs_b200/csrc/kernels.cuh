@@ -43,11 +43,11 @@ constexpr int kChunk = 248;      // new pair-slots per warp iteration of P1 (8 p
 constexpr int kHalf = 192;       // half block: 12 residues x 16 lanes-steps
 constexpr int kHalfPad = 204;    // 192 pair-slots + 12 mirrored from the next half block
 constexpr int kQueueCap = 512;   // template matches per template case awaiting the gates (overflow: in place)
-constexpr int kCandCap = 176;    // survivors decoded per window
+constexpr int kCandCap = 352;    // survivors decoded per window
 constexpr int kFieldItems = 5 * kCandCap;   // (survivor, try_phase) items whose fields are staged
 constexpr int kLutWords = 12 * 25;          // field-extraction table: (residue of j+19, try_phase, field)
 constexpr int kMaxTile = 8184;   // tile mag indices (< T+2) fit 13 bits; surv words <= 256
-constexpr int kDefaultTile = 7768;   // 21 blocks of 384: 252 (block, residue) items per 256 threads
+constexpr int kDefaultTile = 7384;   // 20 blocks of 384: 16 P1 chunks (2 per warp), 240 P2 tasks, 231 P3 words
 constexpr int kTabWords = 256 + 256 + 64 + 256 + 8;   // CRC-24 field tables (see build_crc_tabs)
 constexpr int kTab56 = 576;
 
@@ -84,9 +84,6 @@ struct ScanParams {
     uint32_t ev_mask;
     unsigned long long ord_first, ord_stride;
     const uint32_t *crc_tabs;
-    uint32_t *hand;            // scan -> decode hand-off ring: per tile 60*WP plane words + 256 survivor words
-    uint32_t tile0;            // first tile of this launch (blockIdx.x is relative to it)
-    uint32_t hand_slot0;       // ring slot of tile0
 };
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -109,6 +106,8 @@ struct ScanSmem {
         o = (o + 15) & ~(size_t)15;
         off_dd = o;                                   // float2 first differences, 204 pair-slots per half block
         dd_words = 2 * kHalfPad * (steps + 1);
+        if (dd_words < kFieldItems * 5)               // later reused as the P4 field buffer
+            dd_words = kFieldItems * 5;
         o += (size_t)dd_words * 4;
         off_planes = o;                               // S[phi][rho][word], de-interleaved mod 12
         o += (size_t)5 * 12 * WP * 4;
@@ -118,34 +117,14 @@ struct ScanSmem {
         o += (size_t)2 * edge_bytes;
         off_surv = o;
         o += (size_t)nw * 4;
-        off_queue = o;
-        o += (size_t)5 * kQueueCap * 2;
-        bytes = (o + 15) & ~(size_t)15;
-        off_tabs = off_lut = off_cand = 0;
-    }
-    __host__ __device__ int hand_words() const { return 60 * WP + 256; }
-};
-
-// shared memory plan of the decode kernel
-struct DecodeSmem {
-    int WP, nw;
-    size_t off_planes, off_tabs, off_lut, off_cand, off_fb, bytes;
-    __host__ __device__ explicit DecodeSmem(int T)
-    {
-        const int steps = (T + kHaloTot + kStep - 1) / kStep;
-        WP = steps + 1;
-        nw = (T + 31) / 32;
-        size_t o = 0;
-        off_planes = o;
-        o += (size_t)60 * WP * 4;
         off_tabs = o;
         o += (size_t)kTabWords * 4;
         off_lut = o;
         o += (size_t)kLutWords * 4;
+        off_queue = o;
+        o += (size_t)5 * kQueueCap * 2;
         off_cand = o;
-        o += (size_t)((kCandCap * 2 + 15) & ~15);
-        off_fb = o;
-        o += (size_t)kFieldItems * 5 * 4;
+        o += (size_t)kCandCap * 2;
         bytes = (o + 15) & ~(size_t)15;
     }
 };
@@ -517,21 +496,29 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     const ScanSmem L(p.T);
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
     u64x *dd2 = reinterpret_cast<u64x *>(smem + L.off_dd);                  // (A, B) first-difference pairs
+    uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd2 is dead)
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.off_lut);         // [12][5][5] field extraction table
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [5][12][WP]
     uint8_t *Rc = smem + L.off_edges;                 // rising-edge bit of every sample (bit i <-> m[i] < m[i+1])
     uint8_t *Fc = Rc + L.edge_bytes;                  // falling-edge bit
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
+    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);     // [5][kQueueCap]
-    __shared__ uint32_t s_qn[5];
+    uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
+    __shared__ uint32_t s_warp_tot[kWarps];
+    __shared__ uint32_t s_base, s_count, s_ok, s_qn[5], s_nlong, s_nshort;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = p.tile0 + blockIdx.x;
+    const uint32_t tile = blockIdx.x;
     const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
     const int k = (int)(tile - b * (uint32_t)p.tiles_per_buffer);
     const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
     const int tile_start = k * p.T;
-    if (tile_start >= len)
-        return;   // the decode kernel records the empty tile
+    if (tile_start >= len) {
+        if (tid == 0)
+            p.tile_dir[tile] = make_uint2(0u, 0u);
+        return;
+    }
     const int npos = min(p.T, len - tile_start);
     const int steps = (npos + kHaloTot + kStep - 1) / kStep;   // 384-blocks actually needed
     const int WP = L.WP;
@@ -629,10 +616,22 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     }
     for (int c = tid; c < L.nw; c += kThreads)
         surv[c] = 0;
+    for (int c = tid; c < kTabWords; c += kThreads)
+        tabs[c] = __ldg(p.crc_tabs + c);
     for (int c = tid; c < 5 * 12; c += kThreads)
         planes[c * WP + steps] = 0;   // pad word read by funnel shifts
     if (tid < 5)
         s_qn[tid] = 0;
+    for (int c = tid; c < kLutWords; c += kThreads) {
+        // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
+        // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream, and whether
+        // the stream index q = A/12 advances by one
+        const int ra = c / 25, tt = (c - 25 * ra) / 5, r = c - 25 * ra - 5 * tt;
+        const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
+        const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
+        const int rr = ra + e5 + zd, wrap = rr >= 12 ? 1 : 0;
+        lut[c] = (uint32_t)((phi * 12 + rr - 12 * wrap) * WP) | ((uint32_t)wrap << 16);
+    }
     __syncthreads();
 
     // ---- P2: correlator sign planes.  One lane = one residue class rho of half block hb of
@@ -753,63 +752,8 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     }
     __syncthreads();
 
-    // ---- hand-off: the five sign planes and the survivor bitmap of this tile go to the
-    // decode kernel through a ring that stays L2 resident
-    {
-        uint32_t *h = p.hand + (size_t)(p.hand_slot0 + blockIdx.x) * (size_t)L.hand_words();
-        for (int c = tid; c < 60 * WP; c += kThreads)
-            h[c] = planes[c];
-        if (tid < L.nw)
-            h[60 * WP + tid] = surv[tid];
-    }
-}
-
-// ================================================================== decode kernel
-// Second half of the per-tile work, latency-bound and light in shared memory, so it runs at
-// high occupancy beside the scan kernel of the next chunk of tiles.
-__global__ void __launch_bounds__(kThreads, 6) decode_kernel(const ScanParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    const DecodeSmem L(p.T);
-    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [5][12][WP]
-    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
-    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.off_lut);         // [12][5][5] field extraction table
-    uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
-    uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_fb);           // staged fields
-    __shared__ uint32_t s_warp_tot[kWarps];
-    __shared__ uint32_t s_base, s_count, s_ok, s_nlong, s_nshort;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = p.tile0 + blockIdx.x;
-    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
-    const int k = (int)(tile - b * (uint32_t)p.tiles_per_buffer);
-    const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
-    const int tile_start = k * p.T;
-    if (tile_start >= len) {
-        if (tid == 0)
-            p.tile_dir[tile] = make_uint2(0u, 0u);
-        return;
-    }
-    const int WP = L.WP;
-    const uint32_t *h = p.hand + (size_t)(p.hand_slot0 + blockIdx.x) * (size_t)(60 * WP + 256);
-    for (int c = tid; c < 60 * WP; c += kThreads)
-        planes[c] = h[c];
-    for (int c = tid; c < kTabWords; c += kThreads)
-        tabs[c] = __ldg(p.crc_tabs + c);
-    for (int c = tid; c < kLutWords; c += kThreads) {
-        // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
-        // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream, and whether
-        // the stream index q = A/12 advances by one
-        const int ra = c / 25, tt = (c - 25 * ra) / 5, r = c - 25 * ra - 5 * tt;
-        const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
-        const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
-        const int rr = ra + e5 + zd, wrap = rr >= 12 ? 1 : 0;
-        lut[c] = (uint32_t)((phi * 12 + rr - 12 * wrap) * WP) | ((uint32_t)wrap << 16);
-    }
-    const uint32_t surv_word = (tid < L.nw) ? h[60 * WP + tid] : 0u;
-
     // ---- P4a: count survivors, reserve pool space (positions are emitted in ascending j)
-    uint32_t wv = surv_word;   // nw <= 256 == kThreads
+    uint32_t wv = (tid < L.nw) ? surv[tid] : 0u;   // nw <= 256 == kThreads
     int my_off;
     {
         const int cnt = __popc(wv);

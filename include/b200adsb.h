@@ -73,13 +73,12 @@ typedef struct {
 
 /* accumulated device time per stage since the last reset (OPT_PROFILE=1) */
 typedef struct {
-    double scan_ms;     /* magnitude + edge bits + correlator sign planes + preamble gate */
+    double scan_ms;     /* fused magnitude+preamble+slice+CRC kernel                     */
     double resolve_ms;  /* event finalise + filter resolve + ordered emit                */
     double h2d_ms, d2h_ms;
     uint64_t scan_launches, other_launches;
     uint64_t samples;   /* IQ samples pushed through the scan kernel                     */
     uint64_t candidates;/* positions that passed all preamble gates                      */
-    double decode_ms;   /* field extraction + CRC-24 + classification kernel (own stream) */
 } b200adsb_timing;
 
 /* ------------------------------------------------------------------ life cycle */
