@@ -50,7 +50,9 @@ struct b200adsb_ctx {
     uint32_t *d_members = nullptr;
     uint32_t *d_ev_keys = nullptr, *d_ev_used = nullptr, *d_ev_tmp = nullptr, *d_new_keys = nullptr;
     unsigned long long *d_ev_ord = nullptr;
-    uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr;
+    uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr, *d_lut = nullptr;
+    uint32_t h_lut[kLutWords];
+    int lut_T = 0;
     uint32_t *d_scalar = nullptr;
 
     uint32_t *d_rec = nullptr, *d_emit_info = nullptr;
@@ -277,7 +279,25 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.ord_first = q.ord_first + (unsigned long long)b0 * q.ord_stride;
     p.ord_stride = q.ord_stride;
     p.crc_tabs = c->d_crc_tabs;
-    const ScanSmem L(q.T);
+    ScanSmem L(q.T);
+    if (c->lut_T != q.T) {
+        // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
+        // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream in
+        // plane[phi][rho][WP], and whether the stream index q = A/12 advances by one
+        for (int i = 0; i < kLutWords; i++) {
+            const int ra = i / 25, tt = (i - 25 * ra) / 5, r = i - 25 * ra - 5 * tt;
+            const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
+            const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
+            const int rr = ra + e5 + zd, wrap = rr >= 12 ? 1 : 0;
+            c->h_lut[i] = (uint32_t)((phi * 12 + rr - 12 * wrap) * L.WP) | ((uint32_t)wrap << 16);
+        }
+        CK(c, cudaStreamSynchronize(c->stream));   // a previous launch may still read the table
+        CK(c, cudaMemcpyAsync(c->d_lut, c->h_lut, sizeof c->h_lut, cudaMemcpyHostToDevice, c->stream));
+        c->lut_T = q.T;
+    }
+    p.lut = c->d_lut;
+    if (const char *ex = getenv("B200ADSB_DEBUG_EXTRA_SMEM"))   // occupancy experiments only
+        L.bytes += (size_t)atoi(ex);
     const uint32_t grid = nb * (uint32_t)q.tpb;
     if (grid == 0)
         return B200ADSB_OK;
@@ -547,6 +567,7 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     CKC(cudaMalloc((void **)&c->d_new_keys, (size_t)B200ADSB_ICAO_FILTER_SIZE * 4));
     CKC(cudaMalloc((void **)&c->d_crc_tabs, kTabWords * 4));
     CKC(cudaMalloc((void **)&c->d_crc256, 256 * 4));
+    CKC(cudaMalloc((void **)&c->d_lut, kLutWords * 4));
     CKC(cudaMalloc((void **)&c->d_scalar, 64));
     {
         uint32_t t[kTabWords], t256[256];
@@ -579,6 +600,7 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_new_keys);
     cudaFree(c->d_crc_tabs);
     cudaFree(c->d_crc256);
+    cudaFree(c->d_lut);
     cudaFree(c->d_scalar);
     cudaFree(c->d_rec);
     cudaFree(c->d_emit_info);

@@ -41,8 +41,9 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 248;      // new pair-slots per warp iteration of P1 (8 per lane, lane 31 overlaps)
 constexpr int kHalf = 192;       // half block: 12 residues x 16 lanes-steps
-constexpr int kHalfPad = 204;    // 192 pair-slots + 12 mirrored from the next half block
-constexpr int kQueueCap = 512;   // template matches per template case awaiting the gates (overflow: in place)
+constexpr int kQuarter = 96;     // P2 task = 8 samples at stride 12 of one residue class
+constexpr int kQuarterPad = 108; // 96 pair-slots + 12 mirrored from the next quarter block (bank skew 12)
+constexpr int kQueueCap = 256;   // template matches per template case awaiting the gates (overflow: in place)
 constexpr int kCandCap = 352;    // survivors decoded per window
 constexpr int kFieldItems = 5 * kCandCap;   // (survivor, try_phase) items whose fields are staged
 constexpr int kLutWords = 12 * 25;          // field-extraction table: (residue of j+19, try_phase, field)
@@ -83,7 +84,8 @@ struct ScanParams {
     uint32_t *ev_used;
     uint32_t ev_mask;
     unsigned long long ord_first, ord_stride;
-    const uint32_t *crc_tabs;
+    const uint32_t *crc_tabs;  // CRC-24 field tables (global memory, L1 resident)
+    const uint32_t *lut;       // [12][5][5] field extraction table for this tile size
 };
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -105,7 +107,7 @@ struct ScanSmem {
         size_t o = (size_t)(MPc + 8) * 2;
         o = (o + 15) & ~(size_t)15;
         off_dd = o;                                   // float2 first differences, 204 pair-slots per half block
-        dd_words = 2 * kHalfPad * (steps + 1);
+        dd_words = 2 * kQuarterPad * (2 * ((steps + 1) / 2) + 1);   // half of the tile per P1/P2 pass
         if (dd_words < kFieldItems * 5)               // later reused as the P4 field buffer
             dd_words = kFieldItems * 5;
         o += (size_t)dd_words * 4;
@@ -117,10 +119,7 @@ struct ScanSmem {
         o += (size_t)2 * edge_bytes;
         off_surv = o;
         o += (size_t)nw * 4;
-        off_tabs = o;
-        o += (size_t)kTabWords * 4;
-        off_lut = o;
-        o += (size_t)kLutWords * 4;
+        off_tabs = off_lut = 0;                       // tables live in global memory (L1)
         off_queue = o;
         o += (size_t)5 * kQueueCap * 2;
         off_cand = o;
@@ -243,11 +242,11 @@ __device__ __forceinline__ uint32_t mulx(uint32_t s)
 }
 __device__ __forceinline__ uint32_t a112(const uint32_t *t, uint32_t f)
 {
-    return t[f & 0xff] ^ t[256 + ((f >> 8) & 0xff)] ^ t[512 + ((f >> 16) & 0x3f)];
+    return __ldg(t + (f & 0xff)) ^ __ldg(t + 256 + ((f >> 8) & 0xff)) ^ __ldg(t + 512 + ((f >> 16) & 0x3f));
 }
 __device__ __forceinline__ uint32_t a56(const uint32_t *t, uint32_t f)
 {
-    return t[kTab56 + (f & 0xff)] ^ t[kTab56 + 256 + ((f >> 8) & 7)];
+    return __ldg(t + kTab56 + (f & 0xff)) ^ __ldg(t + kTab56 + 256 + ((f >> 8) & 7));
 }
 __device__ __forceinline__ uint32_t syn112_fields(const uint32_t *t, const uint32_t f[5])
 {
@@ -490,19 +489,19 @@ __device__ __forceinline__ uint32_t df_of_fields(const uint32_t f[5])
 }
 
 template <bool FROM_MAG>
-__global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
+__global__ void __launch_bounds__(kThreads, 4) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const ScanSmem L(p.T);
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
     u64x *dd2 = reinterpret_cast<u64x *>(smem + L.off_dd);                  // (A, B) first-difference pairs
     uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd2 is dead)
-    uint32_t *lut = reinterpret_cast<uint32_t *>(smem + L.off_lut);         // [12][5][5] field extraction table
+    const uint32_t *lut = p.lut;                                             // [12][5][5] field extraction table
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [5][12][WP]
     uint8_t *Rc = smem + L.off_edges;                 // rising-edge bit of every sample (bit i <-> m[i] < m[i+1])
     uint8_t *Fc = Rc + L.edge_bytes;                  // falling-edge bit
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
-    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + L.off_tabs);
+    const uint32_t *tabs = p.crc_tabs;
     uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);     // [5][kQueueCap]
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
     __shared__ uint32_t s_warp_tot[kWarps];
@@ -523,165 +522,160 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
     const int steps = (npos + kHaloTot + kStep - 1) / kStep;   // 384-blocks actually needed
     const int WP = L.WP;
 
-    // ---- P1: magnitudes (u16), edge bits and first differences -> shared memory.
+    // ---- P1/P2 in two passes over the tile (so that the first-difference buffer holds half
+    // of it and four thread blocks fit one SM).
     // Pair-slot s holds sample s of stream A (tile samples [0, 192H)) and sample 192H+s of
-    // stream B.  A warp takes 248 new pair-slots per iteration, 8 per lane (2 x 2 LDG.128);
-    // lane 31 recomputes the next chunk's first 8 only to hand lane 30 its right neighbour.
+    // stream B.  Pass `ps` covers the half blocks [hb0, hb0+nh) of both streams.
     const int H = steps;
     const int offB = kHalf * H;
-    {
-        const int nslots = kHalf * H + 16;      // + the right neighbours / pad mirror of the last half block
-        const int nchunk = (nslots + kChunk - 1) / kChunk;
-        const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of m[0]
-        const int i0 = tile_start - kHaloFront;                  // data index of m[0]
-        const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
-        const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
-        uint32_t wan[8], wbn[8];
-        if (!FROM_MAG && warp < nchunk) {
-            load_iq8(b32, s0 + warp * kChunk + 8 * lane, len, p.vec_ok, wan);
-            load_iq8(b32, s0 + offB + warp * kChunk + 8 * lane, len, p.vec_ok, wbn);
-        }
-        for (int ch = warp; ch < nchunk; ch += kWarps) {
-            const int sl = ch * kChunk + 8 * lane;
-            u64x r[9];   // (A, B) pairs of f32 bit patterns 0x4B000000 + magnitude = 2^23 + magnitude
-            if (!FROM_MAG) {
-#pragma unroll
-                for (int e = 0; e < 8; e++)
-                    r[e] = mag_pair_fast2(wan[e], wbn[e]);
-                if (ch + kWarps < nchunk) {   // next chunk's loads fly while the stores below drain
-                    load_iq8(b32, s0 + (ch + kWarps) * kChunk + 8 * lane, len, p.vec_ok, wan);
-                    load_iq8(b32, s0 + offB + (ch + kWarps) * kChunk + 8 * lane, len, p.vec_ok, wbn);
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    const int ia = i0 + sl + e, ib = ia + offB;
-                    const uint32_t ma = (ia >= 0 && ia < kMagLen) ? (uint32_t)__ldg(d16 + ia) : 0u;
-                    const uint32_t mb = (ib >= 0 && ib < kMagLen) ? (uint32_t)__ldg(d16 + ib) : 0u;
-                    r[e] = f2_pack(__uint_as_float(0x4B000000u + ma), __uint_as_float(0x4B000000u + mb));
-                }
-            }
-            r[8] = __shfl_down_sync(0xffffffffu, r[0], 1);
-            if (lane < 31 && sl < nslots) {
-                uint32_t ra[8], rb[8];
-                uint32_t fA = 0, fB = 0, rA_ = 0, rB_ = 0;
-                u64x dv[8];
-#pragma unroll
-                for (int e = 0; e < 8; e++) {
-                    float x, y;
-                    f2_unpack(r[e], x, y);
-                    ra[e] = __float_as_uint(x);
-                    rb[e] = __float_as_uint(y);
-                    dv[e] = f2_sub(r[e + 1], r[e]);      // m[i+1]-m[i], exact
-                }
-                // edge bits of these samples (demod_2400.rs:221-317 compares neighbours only)
-#pragma unroll
-                for (int e = 7; e >= 0; e--) {
-                    float x, y, nx, ny;
-                    f2_unpack(dv[e], x, y);
-                    f2_unpack(f2_sub(r[e], r[e + 1]), nx, ny);
-                    fA = __funnelshift_l(__float_as_uint(x), fA, 1);     // m[i+1]-m[i] < 0: falling
-                    fB = __funnelshift_l(__float_as_uint(y), fB, 1);
-                    rA_ = __funnelshift_l(__float_as_uint(nx), rA_, 1);  // rising
-                    rB_ = __funnelshift_l(__float_as_uint(ny), rB_, 1);
-                }
-                if (sl < offB) {   // the extra pair-slots duplicate stream B's first samples
-                    *reinterpret_cast<uint4 *>(mag + sl) =
-                        make_uint4(__byte_perm(ra[0], ra[1], 0x5410), __byte_perm(ra[2], ra[3], 0x5410),
-                                   __byte_perm(ra[4], ra[5], 0x5410), __byte_perm(ra[6], ra[7], 0x5410));
-                    Fc[sl >> 3] = (uint8_t)fA;
-                    Rc[sl >> 3] = (uint8_t)rA_;
-                }
-                *reinterpret_cast<uint4 *>(mag + offB + sl) =
-                    make_uint4(__byte_perm(rb[0], rb[1], 0x5410), __byte_perm(rb[2], rb[3], 0x5410),
-                               __byte_perm(rb[4], rb[5], 0x5410), __byte_perm(rb[6], rb[7], 0x5410));
-                Fc[(offB + sl) >> 3] = (uint8_t)fB;
-                Rc[(offB + sl) >> 3] = (uint8_t)rB_;
-                const int hb = sl / kHalf, off = sl - hb * kHalf;
-                u64x *dst = dd2 + kHalfPad * hb + off;
-#pragma unroll
-                for (int e = 0; e < 8; e += 2)
-                    *reinterpret_cast<ulonglong2 *>(dst + e) = make_ulonglong2(dv[e], dv[e + 1]);
-                if (off < 12 && hb > 0) {   // mirror into the previous half block's pad
-                    u64x *pad = dd2 + kHalfPad * (hb - 1) + kHalf + off;
-                    *reinterpret_cast<ulonglong2 *>(pad) = make_ulonglong2(dv[0], dv[1]);
-                    *reinterpret_cast<ulonglong2 *>(pad + 2) = make_ulonglong2(dv[2], dv[3]);
-                    if (off == 0) {
-                        *reinterpret_cast<ulonglong2 *>(pad + 4) = make_ulonglong2(dv[4], dv[5]);
-                        *reinterpret_cast<ulonglong2 *>(pad + 6) = make_ulonglong2(dv[6], dv[7]);
-                    }
-                }
-            }
-        }
-    }
+    const int Hh = (H + 1) / 2;
     for (int c = tid; c < L.nw; c += kThreads)
         surv[c] = 0;
-    for (int c = tid; c < kTabWords; c += kThreads)
-        tabs[c] = __ldg(p.crc_tabs + c);
     for (int c = tid; c < 5 * 12; c += kThreads)
         planes[c * WP + steps] = 0;   // pad word read by funnel shifts
     if (tid < 5)
         s_qn[tid] = 0;
-    for (int c = tid; c < kLutWords; c += kThreads) {
-        // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
-        // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream, and whether
-        // the stream index q = A/12 advances by one
-        const int ra = c / 25, tt = (c - 25 * ra) / 5, r = c - 25 * ra - 5 * tt;
-        const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
-        const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
-        const int rr = ra + e5 + zd, wrap = rr >= 12 ? 1 : 0;
-        lut[c] = (uint32_t)((phi * 12 + rr - 12 * wrap) * WP) | ((uint32_t)wrap << 16);
-    }
-    __syncthreads();
-
-    // ---- P2: correlator sign planes.  One lane = one residue class rho of half block hb of
-    // stream A and of stream B (hb + H): 16 samples at stride 12 of each, processed as (A, B)
-    // pairs in the packed f32x2 pipe; sign bits are shifted in with funnel shifts.
-    // demod_2400.rs:72-83 on negated first differences u,v,w (so that "x > 0" is a sign bit):
-    //   -[5,-3,-2] = 5u+2v   -[4,-1,-3] = 4u+3v   -[3,1,-4] = 3u+4v   -[2,3,-5] = 2u+5v
-    //   -[1,5,-5,-1] = u+6v+w      (all exact in f32: |.| < 2^20)
-    {
-        const u64x five = f2_pack(5.0f, 5.0f);
-        uint16_t *ph = reinterpret_cast<uint16_t *>(planes);
-        for (int task = tid; task < 12 * H; task += kThreads) {
-            const int hb = task / 12, rho = task - 12 * hb;
-            const u64x *dp = dd2 + kHalfPad * hb + rho;
-            uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+    for (int ps = 0; ps < 2; ps++) {
+        const int hb0 = ps * Hh, nh = min(Hh, H - hb0);
+        if (nh <= 0)
+            break;
+        // ---- P1: magnitudes (u16), edge bits and first differences -> shared memory.  A warp
+        // takes 248 new pair-slots per iteration, 8 per lane (2 x 2 LDG.128); lane 31 recomputes
+        // the next chunk's first 8 only to hand lane 30 its right neighbour.
+        {
+            const int sl0 = kHalf * hb0, own_end = kHalf * (hb0 + nh);
+            const int nslots = kHalf * nh + 16;   // + right neighbours / pad mirror of the last half block
+            const int nchunk = (nslots + kChunk - 1) / kChunk;
+            const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of m[0]
+            const int i0 = tile_start - kHaloFront;                  // data index of m[0]
+            const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
+            const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
+            for (int ch = warp; ch < nchunk; ch += kWarps) {
+                const int rel = ch * kChunk + 8 * lane;   // pair-slot relative to this pass
+                const int sl = sl0 + rel;
+                u64x r[9];   // (A, B) pairs of f32 bit patterns 0x4B000000 + magnitude = 2^23 + magnitude
+                if (!FROM_MAG) {
+                    uint32_t wa[8], wb[8];
+                    load_iq8(b32, s0 + sl, len, p.vec_ok, wa);
+                    load_iq8(b32, s0 + offB + sl, len, p.vec_ok, wb);
 #pragma unroll
-            for (int q = 15; q >= 0; q--) {
-                const u64x u = dp[12 * q], v = dp[12 * q + 1], w = dp[12 * q + 2];
-                const u64x g = f2_sub(v, u);
-                const u64x x0 = f2_fma(u, five, f2_add(v, v));
-                const u64x x1 = f2_add(x0, g), x2 = f2_add(x1, g), x3 = f2_add(x2, g);
-                const u64x x4 = f2_add(f2_add(x3, g), w);
-                float lo, hi;
-                f2_unpack(x0, lo, hi);
-                a0 = __funnelshift_l(__float_as_uint(lo), a0, 1);
-                b0 = __funnelshift_l(__float_as_uint(hi), b0, 1);
-                f2_unpack(x1, lo, hi);
-                a1 = __funnelshift_l(__float_as_uint(lo), a1, 1);
-                b1 = __funnelshift_l(__float_as_uint(hi), b1, 1);
-                f2_unpack(x2, lo, hi);
-                a2 = __funnelshift_l(__float_as_uint(lo), a2, 1);
-                b2 = __funnelshift_l(__float_as_uint(hi), b2, 1);
-                f2_unpack(x3, lo, hi);
-                a3 = __funnelshift_l(__float_as_uint(lo), a3, 1);
-                b3 = __funnelshift_l(__float_as_uint(hi), b3, 1);
-                f2_unpack(x4, lo, hi);
-                a4 = __funnelshift_l(__float_as_uint(lo), a4, 1);
-                b4 = __funnelshift_l(__float_as_uint(hi), b4, 1);
+                    for (int e = 0; e < 8; e++)
+                        r[e] = mag_pair_fast2(wa[e], wb[e]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int ia = i0 + sl + e, ib = ia + offB;
+                        const uint32_t ma = (ia >= 0 && ia < kMagLen) ? (uint32_t)__ldg(d16 + ia) : 0u;
+                        const uint32_t mb = (ib >= 0 && ib < kMagLen) ? (uint32_t)__ldg(d16 + ib) : 0u;
+                        r[e] = f2_pack(__uint_as_float(0x4B000000u + ma), __uint_as_float(0x4B000000u + mb));
+                    }
+                }
+                r[8] = __shfl_down_sync(0xffffffffu, r[0], 1);
+                if (lane < 31 && rel < nslots) {
+                    u64x dv[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++)
+                        dv[e] = f2_sub(r[e + 1], r[e]);      // m[i+1]-m[i], exact
+                    if (sl < own_end) {   // the 16 extra pair-slots belong to the next pass / tile
+                        uint32_t ra[8], rb[8];
+                        uint32_t fA = 0, fB = 0, rA_ = 0, rB_ = 0;
+#pragma unroll
+                        for (int e = 0; e < 8; e++) {
+                            float x, y;
+                            f2_unpack(r[e], x, y);
+                            ra[e] = __float_as_uint(x);
+                            rb[e] = __float_as_uint(y);
+                        }
+                        // edge bits of these samples (demod_2400.rs:221-317 compares neighbours only)
+#pragma unroll
+                        for (int e = 7; e >= 0; e--) {
+                            float x, y, nx, ny;
+                            f2_unpack(dv[e], x, y);
+                            f2_unpack(f2_sub(r[e], r[e + 1]), nx, ny);
+                            fA = __funnelshift_l(__float_as_uint(x), fA, 1);     // m[i+1]-m[i] < 0: falling
+                            fB = __funnelshift_l(__float_as_uint(y), fB, 1);
+                            rA_ = __funnelshift_l(__float_as_uint(nx), rA_, 1);  // rising
+                            rB_ = __funnelshift_l(__float_as_uint(ny), rB_, 1);
+                        }
+                        *reinterpret_cast<uint4 *>(mag + sl) =
+                            make_uint4(__byte_perm(ra[0], ra[1], 0x5410), __byte_perm(ra[2], ra[3], 0x5410),
+                                       __byte_perm(ra[4], ra[5], 0x5410), __byte_perm(ra[6], ra[7], 0x5410));
+                        *reinterpret_cast<uint4 *>(mag + offB + sl) =
+                            make_uint4(__byte_perm(rb[0], rb[1], 0x5410), __byte_perm(rb[2], rb[3], 0x5410),
+                                       __byte_perm(rb[4], rb[5], 0x5410), __byte_perm(rb[6], rb[7], 0x5410));
+                        Fc[sl >> 3] = (uint8_t)fA;
+                        Rc[sl >> 3] = (uint8_t)rA_;
+                        Fc[(offB + sl) >> 3] = (uint8_t)fB;
+                        Rc[(offB + sl) >> 3] = (uint8_t)rB_;
+                    }
+                    const int qb = rel / kQuarter, off = rel - qb * kQuarter;   // quarter block inside this pass
+                    u64x *dst = dd2 + kQuarterPad * qb + off;
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2)
+                        *reinterpret_cast<ulonglong2 *>(dst + e) = make_ulonglong2(dv[e], dv[e + 1]);
+                    if (off < 12 && qb > 0) {   // mirror into the previous quarter block's pad
+                        u64x *pad = dd2 + kQuarterPad * (qb - 1) + kQuarter + off;
+                        *reinterpret_cast<ulonglong2 *>(pad) = make_ulonglong2(dv[0], dv[1]);
+                        *reinterpret_cast<ulonglong2 *>(pad + 2) = make_ulonglong2(dv[2], dv[3]);
+                        if (off == 0) {
+                            *reinterpret_cast<ulonglong2 *>(pad + 4) = make_ulonglong2(dv[4], dv[5]);
+                            *reinterpret_cast<ulonglong2 *>(pad + 6) = make_ulonglong2(dv[6], dv[7]);
+                        }
+                    }
+                }
             }
-            // stream bit q = 16*hb + step: 16 bits per half block
-            uint16_t *pa = ph + 2 * (rho * WP) + hb, *pb = pa + H;
-            const int ps = 2 * 12 * WP;
-            pa[0 * ps] = (uint16_t)a0; pb[0 * ps] = (uint16_t)b0;
-            pa[1 * ps] = (uint16_t)a1; pb[1 * ps] = (uint16_t)b1;
-            pa[2 * ps] = (uint16_t)a2; pb[2 * ps] = (uint16_t)b2;
-            pa[3 * ps] = (uint16_t)a3; pb[3 * ps] = (uint16_t)b3;
-            pa[4 * ps] = (uint16_t)a4; pb[4 * ps] = (uint16_t)b4;
         }
+        __syncthreads();
+
+        // ---- P2: correlator sign planes.  One lane = 8 samples at stride 12 (residue class rho,
+        // steps 8*sub..8*sub+7) of half block hb of stream A and of stream B, processed as
+        // (A, B) pairs in the packed f32x2 pipe; sign bits are shifted in with funnel shifts.
+        // demod_2400.rs:72-83 on negated first differences u,v,w (so that "x > 0" is a sign bit):
+        //   -[5,-3,-2] = 5u+2v   -[4,-1,-3] = 4u+3v   -[3,1,-4] = 3u+4v   -[2,3,-5] = 2u+5v
+        //   -[1,5,-5,-1] = u+6v+w      (all exact in f32: |.| < 2^20)
+        {
+            const u64x five = f2_pack(5.0f, 5.0f);
+            uint8_t *pbytes = reinterpret_cast<uint8_t *>(planes);
+            for (int task = tid; task < 24 * nh; task += kThreads) {
+                const int qb = task / 12, rho = task - 12 * qb;
+                const u64x *dp = dd2 + kQuarterPad * qb + rho;
+                uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;
+#pragma unroll
+                for (int q = 7; q >= 0; q--) {
+                    const u64x u = dp[12 * q], v = dp[12 * q + 1], w = dp[12 * q + 2];
+                    const u64x g = f2_sub(v, u);
+                    const u64x x0 = f2_fma(u, five, f2_add(v, v));
+                    const u64x x1 = f2_add(x0, g), x2 = f2_add(x1, g), x3 = f2_add(x2, g);
+                    const u64x x4 = f2_add(f2_add(x3, g), w);
+                    float lo, hi;
+                    f2_unpack(x0, lo, hi);
+                    a0 = __funnelshift_l(__float_as_uint(lo), a0, 1);
+                    b0 = __funnelshift_l(__float_as_uint(hi), b0, 1);
+                    f2_unpack(x1, lo, hi);
+                    a1 = __funnelshift_l(__float_as_uint(lo), a1, 1);
+                    b1 = __funnelshift_l(__float_as_uint(hi), b1, 1);
+                    f2_unpack(x2, lo, hi);
+                    a2 = __funnelshift_l(__float_as_uint(lo), a2, 1);
+                    b2 = __funnelshift_l(__float_as_uint(hi), b2, 1);
+                    f2_unpack(x3, lo, hi);
+                    a3 = __funnelshift_l(__float_as_uint(lo), a3, 1);
+                    b3 = __funnelshift_l(__float_as_uint(hi), b3, 1);
+                    f2_unpack(x4, lo, hi);
+                    a4 = __funnelshift_l(__float_as_uint(lo), a4, 1);
+                    b4 = __funnelshift_l(__float_as_uint(hi), b4, 1);
+                }
+                // stream bit q = 8*(2*hb0 + qb) + step: one byte per task and stream
+                uint8_t *pa = pbytes + 4 * (rho * WP) + 2 * hb0 + qb, *pb = pa + 2 * H;
+                const int pstride = 4 * 12 * WP;
+                pa[0 * pstride] = (uint8_t)a0; pb[0 * pstride] = (uint8_t)b0;
+                pa[1 * pstride] = (uint8_t)a1; pb[1 * pstride] = (uint8_t)b1;
+                pa[2 * pstride] = (uint8_t)a2; pb[2 * pstride] = (uint8_t)b2;
+                pa[3 * pstride] = (uint8_t)a3; pb[3 * pstride] = (uint8_t)b3;
+                pa[4 * pstride] = (uint8_t)a4; pb[4 * pstride] = (uint8_t)b4;
+            }
+        }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- P3a: preamble templates on the edge bitmaps, 32 consecutive positions per thread;
     // matches go to one queue per template case
@@ -829,7 +823,7 @@ __global__ void __launch_bounds__(kThreads, 3) scan_kernel(const ScanParams p)
             uint32_t f[5];
 #pragma unroll
             for (int r = 0; r < 5; r++) {
-                const uint32_t e = lrow[r];
+                const uint32_t e = __ldg(lrow + r);
                 const int q = qA + (int)(e >> 16);
                 const uint32_t *st = planes + (e & 0xffffu) + (q >> 5);
                 f[r] = __funnelshift_r(st[0], st[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
