@@ -44,7 +44,7 @@ constexpr int kHalf = 192;       // half block: 12 residues x 16 lanes-steps
 constexpr int kQuarter = 96;     // P2 task = 8 samples at stride 12 of one residue class
 constexpr int kQuarterPad = 108; // 96 pair-slots + 12 mirrored from the next quarter block (bank skew 12)
 constexpr int kQueueCap = 256;   // template matches per template case awaiting the gates (overflow: in place)
-constexpr int kCandCap = 352;    // survivors decoded per window
+constexpr int kCandCap = 176;    // survivors decoded per window
 constexpr int kFieldItems = 5 * kCandCap;   // (survivor, try_phase) items whose fields are staged
 constexpr int kLutWords = 12 * 25;          // field-extraction table: (residue of j+19, try_phase, field)
 constexpr int kMaxTile = 8184;   // tile mag indices (< T+2) fit 13 bits; surv words <= 256
