@@ -489,7 +489,7 @@ __device__ __forceinline__ uint32_t df_of_fields(const uint32_t f[5])
 }
 
 template <bool FROM_MAG>
-__global__ void __launch_bounds__(kThreads, 4) scan_kernel(const ScanParams p)
+__global__ void __launch_bounds__(kThreads, 5) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const ScanSmem L(p.T);
