@@ -296,6 +296,15 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
         c->lut_T = q.T;
     }
     p.lut = c->d_lut;
+    p.off_dd = (uint32_t)L.off_dd;
+    p.off_planes = (uint32_t)L.off_planes;
+    p.off_edges = (uint32_t)L.off_edges;
+    p.edge_bytes = (uint32_t)L.edge_bytes;
+    p.off_surv = (uint32_t)L.off_surv;
+    p.off_queue = (uint32_t)L.off_queue;
+    p.off_cand = (uint32_t)L.off_cand;
+    p.WP = L.WP;
+    p.nw = L.nw;
     if (const char *ex = getenv("B200ADSB_DEBUG_EXTRA_SMEM"))   // occupancy experiments only
         L.bytes += (size_t)atoi(ex);
     const uint32_t grid = nb * (uint32_t)q.tpb;

@@ -86,6 +86,9 @@ struct ScanParams {
     unsigned long long ord_first, ord_stride;
     const uint32_t *crc_tabs;  // CRC-24 field tables (global memory, L1 resident)
     const uint32_t *lut;       // [12][5][5] field extraction table for this tile size
+    // shared memory layout of ScanSmem(T), computed once on the host
+    uint32_t off_dd, off_planes, off_edges, edge_bytes, off_surv, off_queue, off_cand;
+    int WP, nw;
 };
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -492,7 +495,7 @@ template <bool FROM_MAG>
 __global__ void __launch_bounds__(kThreads, 5) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const ScanSmem L(p.T);
+    const ScanParams &L = p;   // layout fields
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
     u64x *dd2 = reinterpret_cast<u64x *>(smem + L.off_dd);                  // (A, B) first-difference pairs
     uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd2 is dead)
@@ -830,28 +833,44 @@ __global__ void __launch_bounds__(kThreads, 5) scan_kernel(const ScanParams p)
             }
             if (tt == 0)
                 rec_w[6 * c] = (uint32_t)(tile_start + jl);
+            // class of the item: 0 = decided here, 1 = needs the 112-bit syndrome, 2 = the 56-bit one
             uint32_t wd = 0;
-            bool staged = false;
+            int cls = 0;
             if ((f[0] | f[1] | f[2] | f[3] | f[4]) == 0) {
                 wd = kNoneMarker;                      // all 14 bytes zero -> None (mode_s/mod.rs:51-53)
             } else {
                 const uint32_t bit = 1u << df_of_fields(f);
-                const bool is_long = (bit & 0xFF370000u) != 0;    // DF 16,17,18,20,21,24..31
-                const bool is_short = (bit & 0x00000831u) != 0;   // DF 0,4,5,11
-                if (is_long || is_short) {
-                    const uint32_t slot = is_long ? atomicAdd(&s_nlong, 1u)
-                                                  : (uint32_t)(kFieldItems - 1) - atomicAdd(&s_nshort, 1u);
-                    uint32_t *o = fb + 5 * slot;
-                    o[0] = f[0];
-                    o[1] = f[1];
-                    o[2] = f[2] | (((uint32_t)item & 0x3ffu) << 22);
-                    o[3] = f[3] | (((uint32_t)item >> 10) << 22);
-                    o[4] = f[4];
-                    staged = true;
-                }
+                if (bit & 0xFF370000u)                 // DF 16,17,18,20,21,24..31
+                    cls = 1;
+                else if (bit & 0x00000831u)            // DF 0,4,5,11
+                    cls = 2;
             }
-            if (!staged)
+            // one shared-memory atomic per warp and class instead of one per item
+            const unsigned act = __activemask();
+            const unsigned ml = __ballot_sync(act, cls == 1), ms = __ballot_sync(act, cls == 2);
+            const int leader = __ffs(act) - 1;
+            uint32_t basel = 0, bases = 0;
+            if (lane == leader) {
+                if (ml)
+                    basel = atomicAdd(&s_nlong, (uint32_t)__popc(ml));
+                if (ms)
+                    bases = atomicAdd(&s_nshort, (uint32_t)__popc(ms));
+            }
+            basel = __shfl_sync(act, basel, leader);
+            bases = __shfl_sync(act, bases, leader);
+            const unsigned lt = (1u << lane) - 1u;
+            if (cls) {
+                const uint32_t slot = cls == 1 ? basel + (uint32_t)__popc(ml & lt)
+                                               : (uint32_t)(kFieldItems - 1) - (bases + (uint32_t)__popc(ms & lt));
+                uint32_t *o = fb + 5 * slot;
+                o[0] = f[0];
+                o[1] = f[1];
+                o[2] = f[2] | (((uint32_t)item & 0x3ffu) << 22);
+                o[3] = f[3] | (((uint32_t)item >> 10) << 22);
+                o[4] = f[4];
+            } else {
                 rec_w[6 * c + 1 + tt] = wd;
+            }
         }
         __syncthreads();
         {
