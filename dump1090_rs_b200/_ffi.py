@@ -124,11 +124,12 @@ def lib():
     """Load libb200adsb.so; raises if it has not been built (no fallback)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(SO_PATH):
+        so = os.environ.get("B200ADSB_LIB", SO_PATH)   # A/B experiments load a variant build
+        if not os.path.exists(so):
             raise ImportError(
                 f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(the CUDA library is the product; there is no CPU fallback)")
-        L = C.CDLL(SO_PATH)
+        L = C.CDLL(so)
         for name, (res, args) in _PROTOS.items():
             fn = getattr(L, name)
             fn.restype = res

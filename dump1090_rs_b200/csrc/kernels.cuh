@@ -29,6 +29,14 @@
 
 #include "../../include/b200adsb.h"
 
+// build-time experiment knobs (scripts/ab.sh compiles variants with -D...)
+#ifndef B200_SCAN_MIN_BLOCKS
+#define B200_SCAN_MIN_BLOCKS 5
+#endif
+#ifndef B200_AGG_ATOMICS
+#define B200_AGG_ATOMICS 1
+#endif
+
 namespace b200 {
 
 constexpr int kTrailing = B200ADSB_TRAILING_SAMPLES;          // lib.rs:24
@@ -492,7 +500,7 @@ __device__ __forceinline__ uint32_t df_of_fields(const uint32_t f[5])
 }
 
 template <bool FROM_MAG>
-__global__ void __launch_bounds__(kThreads, 5) scan_kernel(const ScanParams p)
+__global__ void __launch_bounds__(kThreads, B200_SCAN_MIN_BLOCKS) scan_kernel(const ScanParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const ScanParams &L = p;   // layout fields
@@ -845,6 +853,7 @@ __global__ void __launch_bounds__(kThreads, 5) scan_kernel(const ScanParams p)
                 else if (bit & 0x00000831u)            // DF 0,4,5,11
                     cls = 2;
             }
+#if B200_AGG_ATOMICS
             // one shared-memory atomic per warp and class instead of one per item
             const unsigned act = __activemask();
             const unsigned ml = __ballot_sync(act, cls == 1), ms = __ballot_sync(act, cls == 2);
@@ -859,9 +868,15 @@ __global__ void __launch_bounds__(kThreads, 5) scan_kernel(const ScanParams p)
             basel = __shfl_sync(act, basel, leader);
             bases = __shfl_sync(act, bases, leader);
             const unsigned lt = (1u << lane) - 1u;
+#endif
             if (cls) {
+#if B200_AGG_ATOMICS
                 const uint32_t slot = cls == 1 ? basel + (uint32_t)__popc(ml & lt)
                                                : (uint32_t)(kFieldItems - 1) - (bases + (uint32_t)__popc(ms & lt));
+#else
+                const uint32_t slot = cls == 1 ? atomicAdd(&s_nlong, 1u)
+                                               : (uint32_t)(kFieldItems - 1) - atomicAdd(&s_nshort, 1u);
+#endif
                 uint32_t *o = fb + 5 * slot;
                 o[0] = f[0];
                 o[1] = f[1];
