@@ -20,6 +20,7 @@ using namespace b200;
 namespace {
 
 constexpr uint32_t kEvSlots = 1u << 16;
+constexpr int kRedo = 1;   // internal status: the optimistic scan overflowed, redo with a larger pool
 constexpr size_t kMaxStageBytes = 2ull << 30;   // host batch API: IQ staged per pass
 
 struct EventPair {
@@ -405,28 +406,6 @@ int scan_run_all(b200adsb_ctx *c)
     return B200ADSB_ERR_NOMEM;
 }
 
-int check_scan_flags(b200adsb_ctx *c, bool *redo)
-{
-    *redo = false;
-    int rc = read_counters(c);
-    if (rc) return rc;
-    const uint32_t flags = c->h_counters[C_FLAGS];
-    if (flags & F_EV_OVF) {
-        clear_events(c);
-        c->cur.active = false;
-        return B200ADSB_ERR_EVENTS;
-    }
-    if (flags & F_POOL_OVF) {
-        rc = clear_events(c);
-        if (rc) return rc;
-        const size_t need = (size_t)c->h_counters[C_POOL];
-        rc = ensure_pool(c, need + need / 8 + 1024);
-        if (rc) return rc;
-        *redo = true;
-    }
-    return B200ADSB_OK;
-}
-
 // stage 2: finalise events, resolve, ordered emit, commit
 int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
                 uint32_t *d_per_buffer_counts)
@@ -494,13 +473,44 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     prof_end(c, c->other_events);
     c->timing.other_launches += 5;
     int rc = read_counters(c);
+    if (rc) { q.active = false; return rc; }
+    if (c->h_counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF))
+        return kRedo;   // optimistic scan overflowed: nothing was committed, the caller redoes it
     q.active = false;
-    if (rc) return rc;
     c->timing.candidates += c->h_counters[C_CAND];
     const size_t n = c->h_counters[C_FRAMES];
     if (n_out)
         *n_out = n;
     return n > cap ? B200ADSB_ERR_CAPACITY : B200ADSB_OK;
+}
+
+// stage 1 without a host round trip + stage 2; if the scan turns out to have overflowed the
+// candidate pool (rare: the pool is sized at ~3x the typical survivor rate and grows), redo it
+// with the checked path.  `scanned` = stage 1 has already been launched by the caller.
+int scan_resolve(b200adsb_ctx *c, bool scanned, b200adsb_frame *d_out, size_t cap, size_t *n_out,
+                 uint32_t *d_per_buffer_counts)
+{
+    int rc;
+    if (!scanned) {
+        rc = reset_scan_counters(c);
+        if (rc) return rc;
+        rc = launch_scan(c, 0, c->cur.n_buffers);
+        if (rc) { c->cur.active = false; return rc; }
+    }
+    rc = resolve_run(c, d_out, cap, n_out, d_per_buffer_counts);
+    if (rc != kRedo)
+        return rc;
+    if (c->h_counters[C_FLAGS] & F_EV_OVF) {
+        c->cur.active = false;
+        return B200ADSB_ERR_EVENTS;
+    }
+    const size_t need = (size_t)c->h_counters[C_POOL];
+    rc = ensure_pool(c, need + need / 8 + 1024);
+    if (rc) { c->cur.active = false; return rc; }
+    rc = scan_run_all(c);
+    if (rc) { c->cur.active = false; return rc; }
+    rc = resolve_run(c, d_out, cap, n_out, d_per_buffer_counts);
+    return rc == kRedo ? B200ADSB_ERR_NOMEM : rc;
 }
 
 int ensure_stage(b200adsb_ctx *c, size_t bytes)
@@ -795,10 +805,14 @@ int b200adsb_demod_iq_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_b
 {
     if (!c)
         return B200ADSB_ERR_BAD_ARG;
-    int rc = b200adsb_scan_batch_dev(c, d_iq, n_buffers, spb, stride, d_lengths, c->next_ordinal, 1);
+    if ((!d_iq && n_buffers && spb) || (stride < spb && n_buffers > 1))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = scan_begin(c, d_iq, false, n_buffers, spb, stride, d_lengths, c->next_ordinal, 1);
     if (rc) return rc;
     c->next_ordinal += n_buffers;
-    return resolve_run(c, d_out, cap, n_out, d_per_buffer_counts);
+    return scan_resolve(c, false, d_out, cap, n_out, d_per_buffer_counts);
 }
 
 // ------------------------------------------------------------------ host batch
@@ -866,15 +880,8 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers
             rc = launch_scan(c, (uint32_t)b0, (uint32_t)cb);
             if (rc) { c->cur.active = false; return rc; }
         }
-        bool redo = false;
-        rc = check_scan_flags(c, &redo);
-        if (rc) return rc;
-        if (redo) {                      // data is resident now: plain re-run
-            rc = scan_run_all(c);
-            if (rc) { c->cur.active = false; return rc; }
-        }
-        size_t n = 0;
-        rc = resolve_run(c, c->d_frames, room, &n, per_buffer_counts ? c->d_counts : nullptr);
+        size_t n = 0;   // (if the pool overflowed the data is resident by now: plain re-run inside)
+        rc = scan_resolve(c, true, c->d_frames, room, &n, per_buffer_counts ? c->d_counts : nullptr);
         if (rc && rc != B200ADSB_ERR_CAPACITY)
             return rc;
         if (rc == B200ADSB_ERR_CAPACITY)
@@ -920,11 +927,9 @@ int b200adsb_demodulate2400(b200adsb_ctx *c, const uint16_t *data, size_t length
     CK(c, cudaMemcpyAsync(c->d_stage, data, (size_t)kMagLen * 2, cudaMemcpyHostToDevice, c->stream));
     rc = scan_begin(c, c->d_stage, true, 1, length, kMagLen, nullptr, c->next_ordinal, 1);
     if (rc) return rc;
-    rc = scan_run_all(c);
-    if (rc) { c->cur.active = false; return rc; }
     c->next_ordinal += 1;
     size_t n = 0;
-    rc = resolve_run(c, c->d_frames, cap, &n, nullptr);
+    rc = scan_resolve(c, false, c->d_frames, cap, &n, nullptr);
     if (rc && rc != B200ADSB_ERR_CAPACITY)
         return rc;
     const size_t ncopy = std::min(n, cap);
@@ -960,8 +965,7 @@ int b200adsb_icao_flush(b200adsb_ctx *c)
     if (rc) return rc;
     CK(c, cudaMemsetAsync(c->d_members, 0, kMemberSlots * 4, c->stream));
     CK(c, cudaMemsetAsync(c->d_counters + C_MEMBERS, 0, 4, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    return B200ADSB_OK;
+    return B200ADSB_OK;   // stream ordered: later calls on this context see the empty filter
 }
 
 int b200adsb_icao_filter_add(b200adsb_ctx *c, uint32_t addr)

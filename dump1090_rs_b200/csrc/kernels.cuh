@@ -1078,7 +1078,10 @@ __global__ void __launch_bounds__(1024) events_commit_kernel(
     uint32_t *ev_keys, unsigned long long *ev_ord, const uint32_t *ev_used, const uint32_t *new_keys,
     uint32_t *counters, uint32_t *members)
 {
-    const uint32_t n = counters[C_EV_USED], adm = counters[C_ADMIT];
+    // a scan that overflowed the candidate pool or the event table is redone by the host:
+    // nothing of it may reach the filter
+    const bool bad = (counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF)) != 0;
+    const uint32_t n = counters[C_EV_USED], adm = bad ? 0u : counters[C_ADMIT];
     for (uint32_t i = threadIdx.x; i < adm; i += blockDim.x)
         members_insert(members, new_keys[i]);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
