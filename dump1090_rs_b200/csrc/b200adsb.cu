@@ -60,7 +60,7 @@ struct b200adsb_ctx {
     int32_t *d_rec_score = nullptr;
     size_t pool_cap = 0;
     uint2 *d_tile_dir = nullptr;
-    uint32_t *d_tile_emit = nullptr;
+    uint32_t *d_tile_emit = nullptr, *d_cta_sum = nullptr, *d_bloom = nullptr;
     size_t tiles_cap = 0;
 
     void *d_stage = nullptr;
@@ -181,11 +181,14 @@ int ensure_tiles(b200adsb_ctx *c, size_t n_tiles)
         return B200ADSB_OK;
     if (c->d_tile_dir) CK(c, cudaFree(c->d_tile_dir));
     if (c->d_tile_emit) CK(c, cudaFree(c->d_tile_emit));
+    if (c->d_cta_sum) CK(c, cudaFree(c->d_cta_sum));
+    c->d_cta_sum = nullptr;
     c->d_tile_dir = nullptr;
     c->d_tile_emit = nullptr;
     c->tiles_cap = 0;
     cudaError_t e = cudaMalloc((void **)&c->d_tile_dir, n_tiles * sizeof(uint2));
     if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_tile_emit, (n_tiles + 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&c->d_cta_sum, (n_tiles / 32 + 2) * 4);
     if (e != cudaSuccess) {
         snprintf(c->err, sizeof(c->err), "tile directory (%zu): %s", n_tiles, cudaGetErrorString(e));
         return B200ADSB_ERR_NOMEM;
@@ -416,8 +419,9 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     prof_begin(c, c->other_events);
     events_finalize_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
                                                       c->d_ev_tmp, c->d_new_keys, c->d_counters,
-                                                      c->d_members, kEvSlots - 1);
+                                                      c->d_members, kEvSlots - 1, c->d_bloom);
     CK(c, cudaGetLastError());
+    const uint32_t n_ctas = (q.n_tiles + 31) / 32;
     if (q.n_tiles) {
         ResolveParams rp{};
         rp.rec = c->d_rec;
@@ -426,6 +430,8 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
         rp.tiles_per_buffer = q.tpb;
         rp.emit_info = c->d_emit_info;
         rp.tile_emit = c->d_tile_emit;
+        rp.cta_sum = c->d_cta_sum;
+        rp.bloom = c->d_bloom;
         rp.rec_score = c->d_rec_score;
         rp.members = c->d_members;
         rp.ev_keys = c->d_ev_keys;
@@ -433,15 +439,15 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
         rp.ev_mask = kEvSlots - 1;
         rp.ord_first = q.ord_first;
         rp.ord_stride = q.ord_stride;
-        const uint32_t g = (q.n_tiles + kWarps - 1) / kWarps;
-        resolve_kernel<<<g, kThreads, 0, c->stream>>>(rp);
+        resolve_kernel<<<n_ctas, kResolveThreads, 0, c->stream>>>(rp);
         CK(c, cudaGetLastError());
     }
-    tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_tile_emit, q.n_tiles, c->d_counters);
+    // exclusive scan over the per-block sums (32 tiles each); total -> counters[C_FRAMES]
+    tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_cta_sum, n_ctas, c->d_counters);
     CK(c, cudaGetLastError());
     if (d_per_buffer_counts && q.n_buffers) {
         buffer_counts_kernel<<<(q.n_buffers + 255) / 256, 256, 0, c->stream>>>(
-            c->d_tile_emit, q.n_buffers, q.tpb, q.n_tiles, c->d_counters, d_per_buffer_counts);
+            c->d_tile_emit, q.n_buffers, q.tpb, d_per_buffer_counts);
         CK(c, cudaGetLastError());
         c->timing.other_launches++;
     }
@@ -454,17 +460,17 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
         ep.rec = c->d_rec;
         ep.tile_dir = c->d_tile_dir;
         ep.emit_info = c->d_emit_info;
-        ep.tile_excl = c->d_tile_emit;
+        ep.tile_cnt = c->d_tile_emit;
+        ep.cta_excl = c->d_cta_sum;
         ep.n_tiles = q.n_tiles;
         ep.tiles_per_buffer = q.tpb;
         ep.out = d_out;
         ep.cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
         ep.msgs = q.msgs;
-        const uint32_t g = (q.n_tiles + kWarps - 1) / kWarps;
         if (q.from_mag)
-            emit_kernel<true><<<g, kThreads, 0, c->stream>>>(ep);
+            emit_kernel<true><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
         else
-            emit_kernel<false><<<g, kThreads, 0, c->stream>>>(ep);
+            emit_kernel<false><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
         CK(c, cudaGetLastError());
     }
     events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
@@ -587,6 +593,7 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     CKC(cudaMalloc((void **)&c->d_crc_tabs, kTabWords * 4));
     CKC(cudaMalloc((void **)&c->d_crc256, 256 * 4));
     CKC(cudaMalloc((void **)&c->d_lut, kLutWords * 4));
+    CKC(cudaMalloc((void **)&c->d_bloom, kBloomWords * 4));
     CKC(cudaMalloc((void **)&c->d_scalar, 64));
     {
         uint32_t t[kTabWords], t256[256];
@@ -626,6 +633,8 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_rec_score);
     cudaFree(c->d_tile_dir);
     cudaFree(c->d_tile_emit);
+    cudaFree(c->d_cta_sum);
+    cudaFree(c->d_bloom);
     cudaFree(c->d_stage);
     cudaFree(c->d_frames);
     cudaFree(c->d_counts);

@@ -376,6 +376,16 @@ __device__ inline void event_add(uint32_t *ev_keys, unsigned long long *ev_ord, 
     atomicOr(&counters[C_FLAGS], F_EV_OVF);
 }
 
+// 64 Kbit membership pre-filter over (filter keys U this batch's event keys): one load rejects
+// the overwhelming majority of address-parity syndromes, which are not aircraft addresses
+constexpr uint32_t kBloomWords = 2048;
+__device__ __forceinline__ uint32_t bloom_bit(uint32_t key) { return (key * 0x9E3779B1u) >> 16; }
+__device__ __forceinline__ bool bloom_hit(const uint32_t *bloom, uint32_t key)
+{
+    const uint32_t h = bloom_bit(key);
+    return (bloom[h >> 5] >> (h & 31)) & 1u;
+}
+
 __device__ __forceinline__ bool members_has(const uint32_t *members, uint32_t key)
 {
     uint32_t h = hash32(key) & (kMemberSlots - 1);
@@ -1022,10 +1032,24 @@ __global__ void events_import_kernel(const unsigned long long *pairs, uint32_t n
 // first 4096 distinct keys by first-add order; later ones are dropped.  One block.
 __global__ void __launch_bounds__(1024) events_finalize_kernel(
     const uint32_t *ev_keys, unsigned long long *ev_ord, const uint32_t *ev_used, uint32_t *ev_tmp,
-    uint32_t *new_keys, uint32_t *counters, const uint32_t *members, uint32_t ev_mask)
+    uint32_t *new_keys, uint32_t *counters, const uint32_t *members, uint32_t ev_mask, uint32_t *bloom)
 {
     const uint32_t n = counters[C_EV_USED];
     const uint32_t have = counters[C_MEMBERS];
+    for (uint32_t i = threadIdx.x; i < kBloomWords; i += blockDim.x)
+        bloom[i] = 0u;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < kMemberSlots; i += blockDim.x) {
+        const uint32_t k = members[i];
+        if (k) {
+            const uint32_t h = bloom_bit(k);
+            atomicOr(&bloom[h >> 5], 1u << (h & 31));
+        }
+    }
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint32_t h = bloom_bit(ev_keys[ev_used[i]]);
+        atomicOr(&bloom[h >> 5], 1u << (h & 31));
+    }
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
         const uint32_t h = ev_used[i];
         const uint32_t key = ev_keys[h];
@@ -1106,6 +1130,8 @@ struct ResolveParams {
     int tiles_per_buffer;
     uint32_t *emit_info;       // per record: 0, or score<<16 | len<<8 | phase
     uint32_t *tile_emit;       // per tile: frames emitted
+    uint32_t *cta_sum;         // per resolve block (32 tiles): frames emitted
+    const uint32_t *bloom;
     int32_t *rec_score;        // nullable: per record best score (diagnostics / message API)
     const uint32_t *members;
     const uint32_t *ev_keys;
@@ -1118,61 +1144,76 @@ __device__ __forceinline__ bool is_member(const ResolveParams &p, uint32_t key, 
 {
     if (key == 0u)
         return true;                         // icao_filter_test(0) (icao_filter.rs:71,78)
+    if (!bloom_hit(p.bloom, key))
+        return false;
     if (members_has(p.members, key))
         return true;
     return event_first(p.ev_keys, p.ev_ord, p.ev_mask, key) < ord;
 }
 
-// one warp per tile; lanes stride over the tile's records
-__global__ void __launch_bounds__(kThreads) resolve_kernel(const ResolveParams p)
+// one warp per tile, 32 tiles per block; lanes stride over the tile's records
+constexpr int kResolveThreads = 1024;
+__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const ResolveParams p)
 {
-    const uint32_t tile = blockIdx.x * kWarps + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (tile >= p.n_tiles)
-        return;
-    const uint2 d = p.tile_dir[tile];
-    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
-    const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
+    __shared__ uint32_t s_cnt[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.x * 32 + warp;
     uint32_t emitted = 0;
-    for (uint32_t i = lane; i < d.y; i += 32) {
-        const uint32_t *r = p.rec + 6ull * (d.x + i);
-        const uint32_t j = r[0];
-        int best = -2;                        // demod_2400.rs:152
-        uint32_t best_t = 0, best_len = 7;
+    if (tile < p.n_tiles) {
+        const uint2 d = p.tile_dir[tile];
+        const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
+        const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
+        for (uint32_t i = lane; i < d.y; i += 32) {
+            const uint32_t *r = p.rec + 6ull * (d.x + i);
+            const uint32_t j = r[0];
+            int best = -2;                        // demod_2400.rs:152
+            uint32_t best_t = 0, best_len = 7;
 #pragma unroll
-        for (int tt = 0; tt < 5; tt++) {
-            const uint32_t wd = r[1 + tt];
-            const uint32_t kind = wd >> 29, key = wd & 0xffffffu;
-            if (kind == K_NONE)
-                continue;
-            const bool m = is_member(p, key, ord_buf | ((unsigned long long)j << 3) | (unsigned)tt);
-            int score;
-            uint32_t len;
-            switch (kind) {                   // mode_s/mod.rs:56-134
-            case K_PAR_SHORT: score = m ? 1000 : -1; len = 7; break;
-            case K_DF11_IID0: score = m ? 1600 : 750; len = 7; break;
-            case K_DF11_IID: score = m ? 1000 : -1; len = 7; break;
-            case K_DF17:
-            case K_DF18: score = m ? 1800 : 1400; len = 14; break;
-            default: score = m ? 1000 : -2; len = 14; break;
+            for (int tt = 0; tt < 5; tt++) {
+                const uint32_t wd = r[1 + tt];
+                const uint32_t kind = wd >> 29, key = wd & 0xffffffu;
+                if (kind == K_NONE)
+                    continue;
+                const bool m = is_member(p, key, ord_buf | ((unsigned long long)j << 3) | (unsigned)tt);
+                int score;
+                uint32_t len;
+                switch (kind) {                   // mode_s/mod.rs:56-134
+                case K_PAR_SHORT: score = m ? 1000 : -1; len = 7; break;
+                case K_DF11_IID0: score = m ? 1600 : 750; len = 7; break;
+                case K_DF11_IID: score = m ? 1000 : -1; len = 7; break;
+                case K_DF17:
+                case K_DF18: score = m ? 1800 : 1400; len = 14; break;
+                default: score = m ? 1000 : -2; len = 14; break;
+                }
+                if (score > best) {               // demod_2400.rs:185 (strict)
+                    best = score;
+                    best_t = (uint32_t)tt;
+                    best_len = len;
+                }
             }
-            if (score > best) {               // demod_2400.rs:185 (strict)
-                best = score;
-                best_t = (uint32_t)tt;
-                best_len = len;
-            }
+            const bool emit = best >= 0;          // demod_2400.rs:203
+            p.emit_info[d.x + i] = emit ? (((uint32_t)best << 16) | (best_len << 8) | (4u + best_t)) : 0u;
+            if (p.rec_score)
+                p.rec_score[d.x + i] = best;
+            emitted += emit ? 1u : 0u;
         }
-        const bool emit = best >= 0;          // demod_2400.rs:203
-        p.emit_info[d.x + i] = emit ? (((uint32_t)best << 16) | (best_len << 8) | (4u + best_t)) : 0u;
-        if (p.rec_score)
-            p.rec_score[d.x + i] = best;
-        emitted += emit ? 1u : 0u;
-    }
 #pragma unroll
-    for (int o = 16; o; o >>= 1)
-        emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
+        for (int o = 16; o; o >>= 1)
+            emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
+        if (lane == 0)
+            p.tile_emit[tile] = emitted;
+    }
     if (lane == 0)
-        p.tile_emit[tile] = emitted;
+        s_cnt[warp] = emitted;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_cnt[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1)
+            v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0)
+            p.cta_sum[blockIdx.x] = v;
+    }
 }
 
 // exclusive scan of tile_emit (in place) by one block; total -> counters[C_FRAMES];
@@ -1223,16 +1264,15 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t *tile_emit, ui
         counters[C_FRAMES] = s_carry;
 }
 
-__global__ void buffer_counts_kernel(const uint32_t *tile_excl, uint32_t n_buffers, int tpb,
-                                     uint32_t n_tiles, const uint32_t *counters, uint32_t *out)
+__global__ void buffer_counts_kernel(const uint32_t *tile_cnt, uint32_t n_buffers, int tpb, uint32_t *out)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_buffers)
         return;
-    const uint32_t lo = tile_excl[(size_t)b * tpb];
-    const uint32_t nx = (b + 1) * (uint32_t)tpb;
-    const uint32_t hi = nx < n_tiles ? tile_excl[nx] : counters[C_FRAMES];
-    out[b] = hi - lo;
+    uint32_t v = 0;
+    for (int k = 0; k < tpb; k++)
+        v += tile_cnt[(size_t)b * tpb + k];
+    out[b] = v;
 }
 
 // ================================================================== emit
@@ -1244,7 +1284,8 @@ struct EmitParams {
     const uint32_t *rec;
     const uint2 *tile_dir;
     const uint32_t *emit_info;
-    const uint32_t *tile_excl;
+    const uint32_t *tile_cnt;    // frames per tile
+    const uint32_t *cta_excl;    // exclusive prefix per block of 32 tiles
     uint32_t n_tiles;
     int tiles_per_buffer;
     b200adsb_frame *out;
@@ -1256,16 +1297,27 @@ struct EmitParams {
 // (src/demod_2400.rs:158-182 in closed form: bit n of try_phase t is decided at
 //  P = 5(j+19)+t+12n, sample P/5, correlator P%5)
 template <bool FROM_MAG>
-__global__ void __launch_bounds__(kThreads) emit_kernel(const EmitParams p)
+__global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams p)
 {
-    __shared__ uint16_t s_mag[kWarps][288];
+    __shared__ uint16_t s_mag[32][288];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile = blockIdx.x * kWarps + warp;
-    if (tile >= p.n_tiles)
+    const uint32_t tile = blockIdx.x * 32 + warp;
+    // this tile's first output slot: block prefix + the counts of the block's earlier tiles
+    const uint32_t t_l = blockIdx.x * 32 + (uint32_t)lane;
+    const uint32_t c_l = t_l < p.n_tiles ? p.tile_cnt[t_l] : 0u;
+    uint32_t incl = c_l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    const uint32_t my_cnt = __shfl_sync(0xffffffffu, c_l, warp);
+    uint32_t out_idx = p.cta_excl[blockIdx.x] + __shfl_sync(0xffffffffu, incl - c_l, warp);
+    if (tile >= p.n_tiles || my_cnt == 0u)
         return;
     const uint2 d = p.tile_dir[tile];
     const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
-    uint32_t out_idx = p.tile_excl[tile];
     const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
     for (uint32_t base = 0; base < d.y; base += 32) {
         const uint32_t i = base + lane;
