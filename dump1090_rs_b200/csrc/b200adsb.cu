@@ -432,7 +432,7 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
         rp.tile_emit = c->d_tile_emit;
         rp.cta_sum = c->d_cta_sum;
         rp.bloom = c->d_bloom;
-        rp.rec_score = c->d_rec_score;
+        rp.rec_score = q.msgs ? c->d_rec_score : nullptr;   // only the message-level API reads scores
         rp.members = c->d_members;
         rp.ev_keys = c->d_ev_keys;
         rp.ev_ord = c->d_ev_ord;

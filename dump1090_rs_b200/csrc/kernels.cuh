@@ -1128,7 +1128,7 @@ struct ResolveParams {
     const uint2 *tile_dir;
     uint32_t n_tiles;
     int tiles_per_buffer;
-    uint32_t *emit_info;       // per record: 0, or score<<16 | len<<8 | phase
+    uint32_t *emit_info;       // per tile (at its pool base): compact list of emitting records
     uint32_t *tile_emit;       // per tile: frames emitted
     uint32_t *cta_sum;         // per resolve block (32 tiles): frames emitted
     const uint32_t *bloom;
@@ -1192,14 +1192,17 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const ResolveP
                 }
             }
             const bool emit = best >= 0;          // demod_2400.rs:203
-            p.emit_info[d.x + i] = emit ? (((uint32_t)best << 16) | (best_len << 8) | (4u + best_t)) : 0u;
             if (p.rec_score)
                 p.rec_score[d.x + i] = best;
-            emitted += emit ? 1u : 0u;
+            // the tile's emitting records, compacted in ascending j at the front of its range:
+            // score<<17 | record index in tile<<4 | long<<3 | try_phase-4
+            const unsigned act = __activemask();
+            const unsigned em = __ballot_sync(act, emit);
+            if (emit)
+                p.emit_info[d.x + emitted + (uint32_t)__popc(em & ((1u << lane) - 1u))] =
+                    ((uint32_t)best << 17) | (i << 4) | ((best_len == 14u ? 1u : 0u) << 3) | best_t;
+            emitted += (uint32_t)__popc(em);
         }
-#pragma unroll
-        for (int o = 16; o; o >>= 1)
-            emitted += __shfl_xor_sync(0xffffffffu, emitted, o);
         if (lane == 0)
             p.tile_emit[tile] = emitted;
     }
@@ -1319,17 +1322,15 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
     const uint2 d = p.tile_dir[tile];
     const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
     const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
-    for (uint32_t base = 0; base < d.y; base += 32) {
+    for (uint32_t base = 0; base < my_cnt; base += 32) {
         const uint32_t i = base + lane;
-        const uint32_t info = i < d.y ? p.emit_info[d.x + i] : 0u;
-        const uint32_t jmine = (i < d.y && info) ? p.rec[6ull * (d.x + i)] : 0u;
-        uint32_t mask = __ballot_sync(0xffffffffu, info != 0u);
-        while (mask) {
-            const int src = __ffs(mask) - 1;
-            mask &= mask - 1;
+        const uint32_t info = i < my_cnt ? p.emit_info[d.x + i] : 0u;
+        const uint32_t jmine = i < my_cnt ? p.rec[6ull * (d.x + ((info >> 4) & 0x1fffu))] : 0u;
+        const int nthis = (int)min(32u, my_cnt - base);
+        for (int src = 0; src < nthis; src++) {
             const uint32_t inf = __shfl_sync(0xffffffffu, info, src);
             const uint32_t j = __shfl_sync(0xffffffffu, jmine, src);
-            const int t = (int)(inf & 0xff), flen = (int)((inf >> 8) & 0xff);
+            const int t = 4 + (int)(inf & 7u), flen = (inf & 8u) ? 14 : 7;
             uint32_t words[4] = {0, 0, 0, 0};
             if (p.msgs == nullptr) {
                 // magnitudes of data[j+19 .. j+19+288)
@@ -1392,7 +1393,7 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
                     for (int wq = 0; wq < 4; wq++)
                         o[wq] = by[4 * wq] | (by[4 * wq + 1] << 8) | (by[4 * wq + 2] << 16) |
                                 ((uint32_t)by[4 * wq + 3] << 24);
-                    o[4] = (inf >> 16) & 0xffffu;   // score (>= 0 here), reserved = 0
+                    o[4] = (inf >> 17) & 0x7fffu;   // score (>= 0 here), reserved = 0
                     o[5] = j;
                     o[6] = b;
                 }
