@@ -149,6 +149,13 @@ class Context:
     def events_import_dev(self, pairs_ptr: int, n: int):
         self._check(self._L.b200adsb_events_import_dev(self._h, pairs_ptr, n), "events_import")
 
+    def events_pack_dev(self, rows_ptr: int, rows_cap: int):
+        self._check(self._L.b200adsb_events_pack_dev(self._h, rows_ptr, rows_cap), "events_pack")
+
+    def events_import_packed_dev(self, gathered_ptr: int, n_ranks: int, rows_per_rank: int, skip_rank: int):
+        self._check(self._L.b200adsb_events_import_packed_dev(self._h, gathered_ptr, n_ranks, rows_per_rank,
+                                                              skip_rank), "events_import_packed")
+
     def resolve_batch_dev(self, out_ptr: int, cap: int, counts_ptr: int = 0) -> int:
         n = C.c_size_t(0)
         self._check(self._L.b200adsb_resolve_batch_dev(self._h, out_ptr, cap, C.byref(n), counts_ptr or None),

@@ -798,6 +798,35 @@ int b200adsb_events_import_dev(b200adsb_ctx *c, const uint64_t *d_pairs, size_t 
     return B200ADSB_OK;
 }
 
+int b200adsb_events_pack_dev(b200adsb_ctx *c, uint64_t *d_rows, size_t rows_cap)
+{
+    if (!c || !d_rows || rows_cap < 2)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    events_pack_kernel<<<16, 256, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used, c->d_counters,
+                                                  (unsigned long long *)d_rows,
+                                                  (uint32_t)std::min<size_t>(rows_cap, 0xffffffffu));
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+int b200adsb_events_import_packed_dev(b200adsb_ctx *c, const uint64_t *d_gathered, size_t n_ranks,
+                                      size_t rows_per_rank, size_t skip_rank)
+{
+    if (!c || !d_gathered || rows_per_rank < 2)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    events_import_packed_kernel<<<16, 256, 0, c->stream>>>(
+        (const unsigned long long *)d_gathered, (uint32_t)n_ranks, (uint32_t)rows_per_rank, (uint32_t)skip_rank,
+        c->d_ev_keys, c->d_ev_ord, c->d_ev_used, kEvSlots - 1, c->d_counters);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
 int b200adsb_resolve_batch_dev(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
                                uint32_t *d_per_buffer_counts)
 {
@@ -805,7 +834,12 @@ int b200adsb_resolve_batch_dev(b200adsb_ctx *c, b200adsb_frame *d_out, size_t ca
         return B200ADSB_ERR_BAD_ARG;
     int rc = bind(c);
     if (rc) return rc;
-    return resolve_run(c, d_out, cap, n_out, d_per_buffer_counts);
+    rc = resolve_run(c, d_out, cap, n_out, d_per_buffer_counts);
+    if (rc == kRedo) {   // only an exchange-buffer or event-table overflow can surface here
+        c->cur.active = false;
+        return B200ADSB_ERR_EVENTS;
+    }
+    return rc;
 }
 
 int b200adsb_demod_iq_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffers, size_t spb,

@@ -1020,6 +1020,44 @@ __global__ void events_export_kernel(const uint32_t *ev_keys, const unsigned lon
         pairs[2ull * i + 1] = ev_ord[h];
     }
 }
+// packed form for a sync-free exchange: rows[0] = (count, 0), rows[1..] = (key, ordinal)
+__global__ void events_pack_kernel(const uint32_t *ev_keys, const unsigned long long *ev_ord,
+                                   const uint32_t *ev_used, const uint32_t *counters,
+                                   unsigned long long *rows, uint32_t rows_cap)
+{
+    const uint32_t n = counters[C_EV_USED];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rows[0] = n;
+        rows[1] = 0;
+    }
+    const uint32_t m = min(n, rows_cap - 1);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const uint32_t h = ev_used[i];
+        rows[2ull * (i + 1)] = ev_keys[h];
+        rows[2ull * (i + 1) + 1] = ev_ord[h];
+    }
+}
+// gathered: n_ranks blocks of rows_per_rank packed rows; merges every block but `skip`
+__global__ void events_import_packed_kernel(const unsigned long long *gathered, uint32_t n_ranks,
+                                            uint32_t rows_per_rank, uint32_t skip, uint32_t *ev_keys,
+                                            unsigned long long *ev_ord, uint32_t *ev_used, uint32_t mask,
+                                            uint32_t *counters)
+{
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        if (r == skip)
+            continue;
+        const unsigned long long *rows = gathered + 2ull * r * rows_per_rank;
+        const unsigned long long n = rows[0];
+        if (n > rows_per_rank - 1) {   // that rank had more events than fit the exchange buffer
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                atomicOr(&counters[C_FLAGS], F_EV_OVF);
+            continue;
+        }
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += gridDim.x * blockDim.x)
+            event_add(ev_keys, ev_ord, ev_used, mask, counters, (uint32_t)rows[2ull * (i + 1)], rows[2ull * (i + 1) + 1]);
+    }
+}
+
 __global__ void events_import_kernel(const unsigned long long *pairs, uint32_t n, uint32_t *ev_keys,
                                      unsigned long long *ev_ord, uint32_t *ev_used, uint32_t mask,
                                      uint32_t *counters)

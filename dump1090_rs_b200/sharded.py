@@ -53,30 +53,34 @@ def exchange_events(pairs, count: int, group=None):
 
 
 class ShardedDemodulator:
-    """This rank's share of a sharded stream: scan -> exchange -> resolve on its Context."""
+    """This rank's share of a sharded stream: scan -> exchange -> resolve on its Context.
 
-    def __init__(self, ctx, rank: int, world: int, group=None, event_cap: int = 4096):
+    The exchange is one fixed-size all-gather on the context's stream with no host round trip:
+    row 0 of each rank's block carries its event count (b200adsb_events_pack_dev /
+    b200adsb_events_import_packed_dev)."""
+
+    def __init__(self, ctx, rank: int, world: int, group=None, event_rows: int = 4096):
         import torch
 
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
-        self.event_cap = event_cap
-        self.pairs = torch.zeros((event_cap, 2), dtype=torch.int64, device=torch.device("cuda", ctx.device))
+        self.event_rows = event_rows
+        dev = torch.device("cuda", ctx.device)
+        self.rows = torch.zeros((event_rows, 2), dtype=torch.int64, device=dev)
+        self.gathered = torch.zeros((world * event_rows, 2), dtype=torch.int64, device=dev)
         self.position = 0          # stream position (in global buffers) of the next batch
 
     def step(self, iq_ptr: int, n_local: int, spb: int, stride: int, out_ptr: int, cap: int,
              n_total: int | None = None, counts_ptr: int = 0) -> int:
         """Demodulates this rank's n_local buffers of a batch of n_total stream buffers
         (default n_local * world); frames (with local buffer indices) go to out_ptr."""
-        import torch
+        import torch.distributed as dist
 
         n_total = n_local * self.world if n_total is None else n_total
         self.ctx.scan_batch_dev(iq_ptr, n_local, spb, stride, self.position + self.rank, self.world)
-        n_ev = self.ctx.events_export_dev(self.pairs.data_ptr(), self.event_cap)
-        remote, m = exchange_events(self.pairs, n_ev, self.group)
-        if m:
-            torch.cuda.current_stream().synchronize()
-            self.ctx.events_import_dev(remote.data_ptr(), m)
-            self.ctx.sync()
+        if self.world > 1:
+            self.ctx.events_pack_dev(self.rows.data_ptr(), self.event_rows)
+            dist.all_gather_into_tensor(self.gathered, self.rows, group=self.group)
+            self.ctx.events_import_packed_dev(self.gathered.data_ptr(), self.world, self.event_rows, self.rank)
         n = self.ctx.resolve_batch_dev(out_ptr, cap, counts_ptr)
         self.position += n_total
         return n

@@ -155,6 +155,12 @@ int b200adsb_events_count(b200adsb_ctx *ctx, size_t *n);
 /* pairs: 2*cap u64 in DEVICE memory: (key, ordinal) per event */
 int b200adsb_events_export_dev(b200adsb_ctx *ctx, uint64_t *d_pairs, size_t cap, size_t *n);
 int b200adsb_events_import_dev(b200adsb_ctx *ctx, const uint64_t *d_pairs, size_t n);
+/* the same exchange without host round trips: rows[0] = (count, 0), rows[1..] = (key, ordinal);
+ * all-gather the fixed-size row blocks, then merge every block but this rank's own.  A rank
+ * with more than rows-1 events makes the later resolve fail with B200ADSB_ERR_EVENTS. */
+int b200adsb_events_pack_dev(b200adsb_ctx *ctx, uint64_t *d_rows, size_t rows_cap);
+int b200adsb_events_import_packed_dev(b200adsb_ctx *ctx, const uint64_t *d_gathered, size_t n_ranks,
+                                      size_t rows_per_rank, size_t skip_rank);
 int b200adsb_resolve_batch_dev(b200adsb_ctx *ctx, b200adsb_frame *d_out, size_t cap,
                                size_t *n_out, uint32_t *d_per_buffer_counts);
 

@@ -363,3 +363,34 @@ def test_cpp_host_mirror_reference_routine(tmp_path, captures, golden_frames):
     assert np.array_equal(utils.read_test_data(path), captures[name])
     out = subprocess.run([exe, path], check=True, capture_output=True, text=True).stdout.split()
     assert out == ["*" + g["hex"] + ";" for g in golden_frames[name]]
+
+
+def test_packed_event_exchange_two_shards(pkg, oracle_mod):
+    """The sync-free form of the exchange (row 0 = count) used by sharded.ShardedDemodulator:
+    two contexts on one GPU, the 'all-gather' done by hand."""
+    import torch
+    from dump1090_rs_b200 import synth
+    nb, rows = 6, 512
+    batch = synth.make_batch(91, nb, msgs_per_buffer=25, icao_pool=5)
+    ref, o = oracle_stream(oracle_mod, list(batch))
+    ctxs = [pkg.Context(0) for _ in range(2)]
+    dev = [torch.from_numpy(np.ascontiguousarray(batch[r::2])).cuda() for r in range(2)]
+    gathered = torch.zeros((2 * rows, 2), dtype=torch.int64, device="cuda")
+    for r in range(2):
+        ctxs[r].scan_batch_dev(dev[r].data_ptr(), nb // 2, 131072, 131072, r, 2)
+        ctxs[r].events_pack_dev(gathered[r * rows:].data_ptr(), rows)
+    torch.cuda.synchronize()
+    assert int(gathered[0, 0]) + int(gathered[rows, 0]) > 0
+    got = []
+    for r in range(2):
+        ctxs[r].events_import_packed_dev(gathered.data_ptr(), 2, rows, r)
+        out = torch.zeros((4096, 28), dtype=torch.uint8, device="cuda")
+        n = ctxs[r].resolve_batch_dev(out.data_ptr(), 4096)
+        for rr in out[:n].cpu().numpy():
+            got.append(dict(buffer=int(rr[24:28].view(np.uint32)[0]) * 2 + r, j=int(rr[20:24].view(np.uint32)[0]),
+                            phase=int(rr[15]), score=int(rr[16:18].view(np.int16)[0]), msg=bytes(rr[: rr[14]])))
+    got.sort(key=lambda f: (f["buffer"], f["j"]))
+    assert frames_key(got) == frames_key(ref)
+    for c in ctxs:
+        assert set(c.icao_snapshot()) == o.members()
+        c.close()
