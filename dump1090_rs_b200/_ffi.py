@@ -115,6 +115,7 @@ _PROTOS = {
     "b200adsb_icao_restore": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200adsb_modes_checksum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "b200adsb_score_modes_messages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "b200adsb_format_avr": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200adsb_debug_crc_tabs": (C.c_int, [C.c_void_p]),
     "b200adsb_debug_mag_sweep": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
 }

@@ -1160,6 +1160,33 @@ int b200adsb_score_modes_messages(b200adsb_ctx *c, const uint8_t *msgs, size_t n
     return B200ADSB_OK;
 }
 
+/* dump1090_rs/src/main.rs:174-176: one "*{hex};\n" line per frame (the AVR text the
+ * reference writes to its TCP clients).  Pure host formatting of frames already demodulated. */
+int b200adsb_format_avr(const b200adsb_frame *frames, size_t n, char *out, size_t cap, size_t *len)
+{
+    if ((!frames && n) || (!out && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    static const char *hexd = "0123456789abcdef";
+    size_t need = 0;
+    for (size_t i = 0; i < n; i++)
+        need += 3 + 2 * (size_t)frames[i].len;
+    if (len)
+        *len = need;
+    if (need > cap)
+        return B200ADSB_ERR_CAPACITY;
+    size_t o = 0;
+    for (size_t i = 0; i < n; i++) {
+        out[o++] = '*';
+        for (unsigned k = 0; k < frames[i].len; k++) {
+            out[o++] = hexd[frames[i].msg[k] >> 4];
+            out[o++] = hexd[frames[i].msg[k] & 15];
+        }
+        out[o++] = ';';
+        out[o++] = '\n';
+    }
+    return B200ADSB_OK;
+}
+
 /* test hook: compares the scan kernel's fast magnitude with the IEEE-intrinsic form of
  * utils.rs:47-55 on all 2^32 (re, im) inputs, on the GPU. */
 int b200adsb_debug_mag_sweep(b200adsb_ctx *c, uint64_t *mismatches, uint32_t *first_bad)

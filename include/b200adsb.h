@@ -184,6 +184,11 @@ int b200adsb_modes_checksum(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n, 
 int b200adsb_score_modes_messages(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n,
                                   uint8_t *lens, int32_t *scores);
 
+/* ------------------------------------------------------- dump1090_rs/src/main.rs:174-176 */
+/* "*{hex};\n" per frame, the AVR text the reference binary sends to its TCP clients (host
+ * formatting only; the listener itself is out of scope).  *len = bytes needed/written. */
+int b200adsb_format_avr(const b200adsb_frame *frames, size_t n, char *out, size_t cap, size_t *len);
+
 /* test hook: exhaustive GPU comparison of the scan kernel's fast magnitude arithmetic
  * with the IEEE-intrinsic statement of src/utils.rs:47-55 over all 2^32 inputs. */
 int b200adsb_debug_mag_sweep(b200adsb_ctx *ctx, uint64_t *mismatches, uint32_t *first_bad);

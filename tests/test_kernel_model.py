@@ -137,3 +137,13 @@ def test_abi_exports_match_header():
     from oracle import oracle as O
     for a in (0, 1, 0xABCDEF, 0xFFFFFF, 0x2ABCDEF):
         assert L.b200adsb_icao_hash(a) == O.icao_hash(a)
+
+
+def test_avr_lines(golden_frames):
+    """main.rs:174-176: "*{hex};\\n" per frame (host formatting, no GPU)."""
+    from dump1090_rs_b200 import avr
+    name = "test_1641427457780"
+    frames = [dict(msg=bytes.fromhex(g["hex"])) for g in golden_frames[name]]
+    txt = avr.format_frames(frames)
+    assert txt == "".join("*%s;\n" % g["hex"] for g in golden_frames[name]).encode()
+    assert avr.format_frames([]) == b""
