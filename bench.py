@@ -47,27 +47,66 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region.  NVML (nvidia_ml_py) is
+    polled in a thread (a query takes well under a millisecond, the timed region only
+    milliseconds); falls back to nvidia-smi when NVML is unavailable."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index: int):
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.source = None
         self._stop = threading.Event()
         self._t = None
+        self._h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nv = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._h = None
+            self.source = "nvidia-smi"
+
+    def _poll_nvml(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for b, name in self.BITS.items():
+            if bits & b:
+                self.reasons.add(name)
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        for line in out.strip().splitlines():
+            r = [x.strip() for x in line.split(",")]
+            self.sm.append(float(r[0]))
+            self.mx.append(float(r[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
+                if self._h is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.0005 if self._h is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -79,20 +118,10 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"], "source": self.source}
+        return {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx), "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": self.source}
 
 
 def run_reference(args) -> int:
@@ -137,7 +166,7 @@ def run_reference(args) -> int:
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buffers", type=int, default=0, help="buffers per rank (default 1000 at N=1, 1024 at N>1)")
@@ -291,7 +320,7 @@ def main() -> int:
                 int(r[16:18].view(np.int16)[0]), bytes(r[: r[14]]).hex()) for r in raw
                if int(r[24:28].view(np.uint32)[0]) < min(8, ns)]
         parity = got == ref
-        iters = 10
+        iters = 120          # ~10 s of single-core work
         O.bench(sample, ns, SAMPLES, 1, 1, False)
         sec, _fr = O.bench(sample, ns, SAMPLES, iters, 1, False)
         cpu = {"value": ns * SAMPLES * iters / sec / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
