@@ -171,6 +171,7 @@ def main() -> int:
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--buffers", type=int, default=0, help="buffers per rank (default 1000 at N=1, 1024 at N>1)")
     ap.add_argument("--msgs", type=int, default=0, help="injected DF17 per buffer in the first 16 buffers")
+    ap.add_argument("--msgs-all", action="store_true", help="repeat the 16 signal buffers over the whole batch (configs[3])")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -204,6 +205,9 @@ def main() -> int:
         k = min(16, nb)
         inj = synth.make_batch(1090, k, msgs_per_buffer=args.msgs, first_index=rank * 1000)
         iq[:k] = torch.from_numpy(inj).to(dev)
+        if args.msgs_all:
+            for b0 in range(k, nb, k):
+                iq[b0:b0 + k] = iq[:min(k, nb - b0)]
     stream = torch.cuda.current_stream()
     ctx = d.Context(local, stream.cuda_stream)
     ctx.set_option(_ffi.OPT_PROFILE, 1)
@@ -336,7 +340,7 @@ def main() -> int:
             "data": "synthetic",
             "config": {"workload": (f"synthetic 2.4Msps CS16 rtl-like noise (sigma 5.5 LSB of 8 bit), {nb} x 512KiB "
                                     f"buffers per GPU per step, {'BASELINE configs[2]' if world == 1 else 'configs[4] round-robin shards + ICAO event all-gather'}"),
-                       "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES, "injected_msgs": args.msgs,
+                       "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES, "injected_msgs": args.msgs, "injected_in_all_buffers": bool(args.msgs_all),
                        "l2": f"inputs {nb * SAMPLES * 4 / 2**20:.0f} MiB per GPU > 126 MB L2 (no flush needed)",
                        "frames_per_step": n_frames[0]},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
