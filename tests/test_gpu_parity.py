@@ -394,3 +394,41 @@ def test_packed_event_exchange_two_shards(pkg, oracle_mod):
     for c in ctxs:
         assert set(c.icao_snapshot()) == o.members()
         c.close()
+
+
+def test_randomized_ragged_streams(pkg, captures, oracle_mod):
+    """Many small random streams: random buffer counts, lengths (0..9000), strides, tile sizes
+    and contents (capture slices with real frames, injected DF17s, full-range noise); every one
+    must equal the sequential reference, including the filter at the end."""
+    from dump1090_rs_b200 import _ffi, synth
+    rng = np.random.default_rng(2024)
+    base = np.concatenate([captures[n] for n in NAMES])
+    dense, _ = synth.make_buffer(5, 0, msgs_per_buffer=120, icao_pool=4)
+    for case in range(24):
+        nb = int(rng.integers(1, 6))
+        spb = int(rng.integers(1, 9000))
+        stride = spb + int(rng.integers(0, 3)) * 4 + (0 if rng.random() < 0.5 else int(rng.integers(0, 7)))
+        lens = [int(rng.integers(0, spb + 1)) for _ in range(nb)]
+        batch = np.full((nb, stride, 2), 777, dtype=np.int16)
+        bufs = []
+        for b in range(nb):
+            kind = rng.integers(0, 3)
+            if kind == 0:      # slice of a real capture around a known frame
+                j0 = int(rng.choice([21915, 68286, 71134, 130601, 131072 + 14611, 262144 + 9323])) - 326 - int(rng.integers(0, 300))
+                src = base[max(j0, 0): max(j0, 0) + lens[b]]
+            elif kind == 1:    # dense synthetic traffic
+                o0 = int(rng.integers(0, 131072 - spb))
+                src = dense[o0:o0 + lens[b]]
+            else:
+                src = synth.full_range_buffer(case, b, n=max(lens[b], 1))[:lens[b]]
+            lens[b] = min(lens[b], len(src))
+            batch[b, :lens[b]] = src[:lens[b]]
+            bufs.append(batch[b, :lens[b]].copy())
+        ref, o = oracle_stream(oracle_mod, bufs)
+        c = pkg.Context(0)
+        if rng.random() < 0.6:
+            c.set_option(_ffi.OPT_TILE, int(rng.choice([8, 24, 88, 472, 856, 2008, 7384])))
+        got = c.demod_iq_batch(batch, nb, spb, stride=stride, lengths=lens)
+        assert frames_key(got) == frames_key(ref), (case, nb, spb, stride, lens)
+        assert set(c.icao_snapshot()) == o.members(), case
+        c.close()
