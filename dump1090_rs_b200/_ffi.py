@@ -22,7 +22,7 @@ MODES_SHORT_MSG_BYTES = 7       # src/lib.rs:26
 ICAO_FILTER_ADSB_NT = 1 << 25   # src/icao_filter.rs:6
 
 OK, ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_EVENTS = 0, -1, -2, -3, -4, -5, -6
-OPT_TILE, OPT_POOL_SHIFT, OPT_PROFILE, OPT_H2D_CHUNK = 1, 2, 3, 4
+OPT_TILE, OPT_POOL_SHIFT, OPT_PROFILE, OPT_H2D_CHUNK, OPT_CARRY = 1, 2, 3, 4, 5
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false",

@@ -45,7 +45,9 @@ struct b200adsb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     bool own_stream = false;
-    int tile_opt = 0, pool_shift = 5, profile = 0, h2d_chunk = 64;
+    int tile_opt = 0, pool_shift = 5, profile = 0, h2d_chunk = 64, carry = 0;
+    uint32_t *d_tail[2] = {nullptr, nullptr};   // carry mode: last 326 IQ samples of the stream (double buffered)
+    int tail_cur = 0;
 
     uint32_t *d_counters = nullptr, *h_counters = nullptr;
     uint32_t *d_members = nullptr;
@@ -300,6 +302,8 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
         c->lut_T = q.T;
     }
     p.lut = c->d_lut;
+    p.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
+    p.tail = c->d_tail[c->tail_cur];
     p.off_dd = (uint32_t)L.off_dd;
     p.off_planes = (uint32_t)L.off_planes;
     p.off_edges = (uint32_t)L.off_edges;
@@ -460,6 +464,8 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
         ep.rec = c->d_rec;
         ep.tile_dir = c->d_tile_dir;
         ep.emit_info = c->d_emit_info;
+        ep.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
+        ep.tail = c->d_tail[c->tail_cur];
         ep.tile_cnt = c->d_tile_emit;
         ep.cta_excl = c->d_cta_sum;
         ep.n_tiles = q.n_tiles;
@@ -473,6 +479,13 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
             emit_kernel<false><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
         CK(c, cudaGetLastError());
     }
+    const bool save_tail = c->carry && !q.from_mag && !q.msgs && q.n_buffers > 0;
+    if (save_tail) {
+        save_tail_kernel<<<1, 352, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride, q.lengths,
+                                                   q.spb, q.n_buffers, c->d_tail[c->tail_cur],
+                                                   c->d_tail[c->tail_cur ^ 1]);
+        CK(c, cudaGetLastError());
+    }
     events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
                                                     c->d_new_keys, c->d_counters, c->d_members);
     CK(c, cudaGetLastError());
@@ -483,6 +496,8 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     if (c->h_counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF))
         return kRedo;   // optimistic scan overflowed: nothing was committed, the caller redoes it
     q.active = false;
+    if (save_tail)
+        c->tail_cur ^= 1;
     c->timing.candidates += c->h_counters[C_CAND];
     const size_t n = c->h_counters[C_FRAMES];
     if (n_out)
@@ -594,6 +609,10 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     CKC(cudaMalloc((void **)&c->d_crc256, 256 * 4));
     CKC(cudaMalloc((void **)&c->d_lut, kLutWords * 4));
     CKC(cudaMalloc((void **)&c->d_bloom, kBloomWords * 4));
+    for (int i = 0; i < 2; i++) {
+        CKC(cudaMalloc((void **)&c->d_tail[i], 352 * 4));
+        CKC(cudaMemset(c->d_tail[i], 0, 352 * 4));
+    }
     CKC(cudaMalloc((void **)&c->d_scalar, 64));
     {
         uint32_t t[kTabWords], t256[256];
@@ -635,6 +654,8 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_tile_emit);
     cudaFree(c->d_cta_sum);
     cudaFree(c->d_bloom);
+    cudaFree(c->d_tail[0]);
+    cudaFree(c->d_tail[1]);
     cudaFree(c->d_stage);
     cudaFree(c->d_frames);
     cudaFree(c->d_counts);
@@ -661,6 +682,12 @@ int b200adsb_ctx_set_option(b200adsb_ctx *c, int option, int64_t value)
         return B200ADSB_OK;
     case B200ADSB_OPT_PROFILE:
         c->profile = value ? 1 : 0;
+        return B200ADSB_OK;
+    case B200ADSB_OPT_CARRY:
+        c->carry = value ? 1 : 0;   // (re)starting continuity: nothing precedes the next buffer
+        if (cudaSetDevice(c->device) != cudaSuccess ||
+            cudaMemsetAsync(c->d_tail[c->tail_cur], 0, 352 * 4, c->stream) != cudaSuccess)
+            return B200ADSB_ERR_CUDA;
         return B200ADSB_OK;
     case B200ADSB_OPT_H2D_CHUNK:
         if (value < 1)

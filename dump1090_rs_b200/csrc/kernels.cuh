@@ -97,6 +97,10 @@ struct ScanParams {
     // shared memory layout of ScanSmem(T), computed once on the host
     uint32_t off_dd, off_planes, off_edges, edge_bytes, off_surv, off_queue, off_cand;
     int WP, nw;
+    // opt-in stream continuity (B200ADSB_OPT_CARRY): the 326 leading MagnitudeBuffer slots of a
+    // buffer hold the previous buffer's last samples instead of zeros
+    int carry;
+    const uint32_t *tail;      // last 326 IQ samples of the stream before this batch
 };
 
 __host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
@@ -444,7 +448,15 @@ __device__ __forceinline__ uint32_t plane_term(const uint32_t *plane, int WP, in
 
 // eight consecutive IQ words of a buffer starting at sample s (zero outside [0, len):
 // magnitude(0, 0) = 0 is exactly the MagnitudeBuffer zero fill, lib.rs:36-44)
-__device__ __forceinline__ void load_iq8(const uint32_t *b32, int s, int len, int vec_ok, uint32_t w[8])
+__device__ __forceinline__ uint32_t iq_word(const uint32_t *b32, int s, int len, const uint32_t *prev, int prev_len)
+{
+    if (s >= 0)
+        return s < len ? __ldg(b32 + s) : 0u;
+    const int k = prev_len + s;          // carry mode: sample s < 0 lives in the previous buffer
+    return (prev != nullptr && k >= 0) ? __ldg(prev + k) : 0u;
+}
+__device__ __forceinline__ void load_iq8(const uint32_t *b32, int s, int len, int vec_ok, const uint32_t *prev,
+                                         int prev_len, uint32_t w[8])
 {
     if (s >= 0 && s + 7 < len && vec_ok) {
         const int4 v0 = __ldg(reinterpret_cast<const int4 *>(b32 + s));
@@ -453,11 +465,24 @@ __device__ __forceinline__ void load_iq8(const uint32_t *b32, int s, int len, in
         w[4] = (uint32_t)v1.x; w[5] = (uint32_t)v1.y; w[6] = (uint32_t)v1.z; w[7] = (uint32_t)v1.w;
     } else {
 #pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int se = s + e;
-            w[e] = (se >= 0 && se < len) ? __ldg(b32 + se) : 0u;
-        }
+        for (int e = 0; e < 8; e++)
+            w[e] = iq_word(b32, s + e, len, prev, prev_len);
     }
+}
+// the buffer whose tail supplies the samples before buffer b in carry mode
+__device__ __forceinline__ const uint32_t *carry_source(const void *in, unsigned long long stride,
+                                                        const uint32_t *lengths, uint32_t spb, uint32_t b,
+                                                        int carry, const uint32_t *tail, int *prev_len)
+{
+    *prev_len = 0;
+    if (!carry)
+        return nullptr;
+    if (b == 0) {
+        *prev_len = kTrailing;
+        return tail;
+    }
+    *prev_len = lengths ? (int)min(lengths[b - 1], spb) : (int)spb;
+    return reinterpret_cast<const uint32_t *>(in) + (unsigned long long)(b - 1) * stride;
 }
 
 // SNR and quiet-zone gates of one template match (demod_2400.rs:129,135-146) with the
@@ -550,6 +575,9 @@ __global__ void __launch_bounds__(kThreads, B200_SCAN_MIN_BLOCKS) scan_kernel(co
     const int H = steps;
     const int offB = kHalf * H;
     const int Hh = (H + 1) / 2;
+    int prev_len;
+    const uint32_t *prev = FROM_MAG ? nullptr
+                                    : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
     for (int c = tid; c < L.nw; c += kThreads)
         surv[c] = 0;
     for (int c = tid; c < 5 * 12; c += kThreads)
@@ -577,8 +605,8 @@ __global__ void __launch_bounds__(kThreads, B200_SCAN_MIN_BLOCKS) scan_kernel(co
                 u64x r[9];   // (A, B) pairs of f32 bit patterns 0x4B000000 + magnitude = 2^23 + magnitude
                 if (!FROM_MAG) {
                     uint32_t wa[8], wb[8];
-                    load_iq8(b32, s0 + sl, len, p.vec_ok, wa);
-                    load_iq8(b32, s0 + offB + sl, len, p.vec_ok, wb);
+                    load_iq8(b32, s0 + sl, len, p.vec_ok, prev, prev_len, wa);
+                    load_iq8(b32, s0 + offB + sl, len, p.vec_ok, prev, prev_len, wb);
 #pragma unroll
                     for (int e = 0; e < 8; e++)
                         r[e] = mag_pair_fast2(wa[e], wb[e]);
@@ -1327,6 +1355,8 @@ struct EmitParams {
     const uint32_t *emit_info;
     const uint32_t *tile_cnt;    // frames per tile
     const uint32_t *cta_excl;    // exclusive prefix per block of 32 tiles
+    int carry;
+    const uint32_t *tail;
     uint32_t n_tiles;
     int tiles_per_buffer;
     b200adsb_frame *out;
@@ -1360,6 +1390,9 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
     const uint2 d = p.tile_dir[tile];
     const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
     const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
+    int prev_len = 0;
+    const uint32_t *prev = (FROM_MAG || p.msgs) ? nullptr
+                                                : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
     for (uint32_t base = 0; base < my_cnt; base += 32) {
         const uint32_t i = base + lane;
         const uint32_t info = i < my_cnt ? p.emit_info[d.x + i] : 0u;
@@ -1382,8 +1415,8 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
                     } else {
                         const uint32_t *bb = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
                         const int s = idx - kTrailing;
-                        if (s >= 0 && s < len)
-                            m = mag_bits_fast(__ldg(bb + s)) & 0xffffu;   // == mag_pair (exhaustively checked)
+                        // == mag_pair (exhaustively checked)
+                        m = mag_bits_fast(iq_word(bb, s, len, prev, prev_len)) & 0xffffu;
                     }
                     s_mag[warp][k] = (uint16_t)m;
                 }
@@ -1439,6 +1472,31 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
             out_idx++;
         }
     }
+}
+
+// carry mode: the last 326 samples of the stream (walking back over this batch's buffers,
+// then into the old tail) become the next batch's leading samples
+__global__ void save_tail_kernel(const uint32_t *in, unsigned long long stride, const uint32_t *lengths,
+                                 uint32_t spb, uint32_t n_buffers, const uint32_t *old_tail, uint32_t *new_tail)
+{
+    const int k = threadIdx.x;
+    if (k >= kTrailing)
+        return;
+    int back = kTrailing - 1 - k;          // 0 = the very last sample of the stream
+    uint32_t w = 0;
+    bool found = false;
+    for (int b = (int)n_buffers - 1; b >= 0 && !found; b--) {
+        const int len = lengths ? (int)min(lengths[b], spb) : (int)spb;
+        if (back < len) {
+            w = in[(unsigned long long)b * stride + (unsigned)(len - 1 - back)];
+            found = true;
+        } else {
+            back -= len;
+        }
+    }
+    if (!found && back < kTrailing)
+        w = old_tail[kTrailing - 1 - back];
+    new_tail[k] = w;
 }
 
 // ================================================================== filter helpers

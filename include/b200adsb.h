@@ -54,7 +54,12 @@ enum {
     B200ADSB_OPT_TILE = 1,        /* output positions per thread block tile (multiple of 8, <= 8184) */
     B200ADSB_OPT_POOL_SHIFT = 2,  /* candidate pool = positions >> shift (grown on demand)    */
     B200ADSB_OPT_PROFILE = 3,     /* 1: bracket kernels with CUDA events (b200adsb_timing)    */
-    B200ADSB_OPT_H2D_CHUNK = 4    /* buffers per host->device pipeline chunk (host batch API) */
+    B200ADSB_OPT_H2D_CHUNK = 4,   /* buffers per host->device pipeline chunk (host batch API) */
+    B200ADSB_OPT_CARRY = 5        /* 1: stream continuity -- the 326 leading MagnitudeBuffer slots of
+                                     a buffer carry the previous buffer's last samples (what the C
+                                     dump1090 did and the reference drops, lib.rs:24,47-50,
+                                     utils.rs:44); recovers frames that straddle two buffers.  Off by
+                                     default: it changes the output relative to the reference.     */
 };
 
 typedef struct b200adsb_ctx b200adsb_ctx;

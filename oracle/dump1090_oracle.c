@@ -230,6 +230,20 @@ int orc_to_mag(const int16_t *iq, size_t n, orc_magbuf *out)
     return 0;
 }
 
+/* Stream-continuity variant (NOT reference behaviour, which zero-fills: utils.rs:44,
+ * lib.rs:36-50): the 326 leading slots hold the magnitudes of the previous buffer's last
+ * samples, as the C dump1090 the crate was translated from did.  prev_tail: 326 (re, im)
+ * pairs, oldest first, or NULL.  Checker for B200ADSB_OPT_CARRY. */
+int orc_to_mag_carry(const int16_t *prev_tail, const int16_t *iq, size_t n, orc_magbuf *out)
+{
+    if (orc_to_mag(iq, n, out) != 0)
+        return -1;
+    if (prev_tail)
+        for (size_t k = 0; k < ORC_TRAILING_SAMPLES; k++)
+            out->data[k] = orc_mag_one(prev_tail[2 * k], prev_tail[2 * k + 1]);
+    return 0;
+}
+
 /* ---------------------------------------------------------------- demod_2400.rs */
 
 /* src/demod_2400.rs:215-321 */

@@ -96,6 +96,8 @@ int orc_score_modes_message(orc_filter *f, const uint8_t *msg, size_t msg_bytes,
  * returns 0, or -1 when n > 131072 (the reference panics, src/lib.rs:48). */
 int orc_to_mag(const int16_t *iq_re_im, size_t n, orc_magbuf *out);    /* :43-58 */
 uint16_t orc_mag_one(int16_t re, int16_t im);                          /* :47-55 */
+/* not reference behaviour: stream continuity (checker for B200ADSB_OPT_CARRY) */
+int orc_to_mag_carry(const int16_t *prev_tail326, const int16_t *iq_re_im, size_t n, orc_magbuf *out);
 
 /* ---- src/demod_2400.rs ---- */
 /* returns 1 and fills high/sig/noise on Some, else 0 */

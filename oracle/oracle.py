@@ -82,6 +82,8 @@ def lib():
             C.POINTER(Filter), C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.orc_to_mag.restype = C.c_int
         L.orc_to_mag.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(MagBuf)]
+        L.orc_to_mag_carry.restype = C.c_int
+        L.orc_to_mag_carry.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(MagBuf)]
         L.orc_mag_one.restype = C.c_uint16
         L.orc_mag_one.argtypes = [C.c_int16, C.c_int16]
         L.orc_check_preamble.restype = C.c_int
@@ -155,6 +157,18 @@ class Oracle:
                  score=out[i].score)
             for i in range(n)
         ]
+
+    def demod_iq_carry(self, iq: np.ndarray):
+        """Stream continuity (not reference behaviour): the previous buffers' last 326 samples
+        fill the leading slots."""
+        a, p, n = _iq_ptr(iq)
+        tail = getattr(self, "_tail", None)
+        if tail is None:
+            tail = np.zeros((TRAILING_SAMPLES, 2), dtype=np.int16)
+        mb = MagBuf()
+        assert self.L.orc_to_mag_carry(tail.ctypes.data_as(C.c_void_p), p, n, C.byref(mb)) == 0
+        self._tail = np.ascontiguousarray(np.concatenate([tail, a.reshape(-1, 2)])[-TRAILING_SAMPLES:])
+        return self.demodulate2400(mb)
 
     def demod_iq(self, iq: np.ndarray, flush: bool = False):
         if flush:

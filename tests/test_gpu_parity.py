@@ -432,3 +432,48 @@ def test_randomized_ragged_streams(pkg, captures, oracle_mod):
         assert frames_key(got) == frames_key(ref), (case, nb, spb, stride, lens)
         assert set(c.icao_snapshot()) == o.members(), case
         c.close()
+
+
+def test_carry_option_stream_continuity(pkg, oracle_mod):
+    """B200ADSB_OPT_CARRY: bit-exact against the oracle's carry variant, buffer by buffer and in
+    one batched call, and invariant under where the stream is cut."""
+    from dump1090_rs_b200 import _ffi, synth
+    stream, _ = synth.make_buffer(31, 0, n=100000, msgs_per_buffer=90, icao_pool=5)
+    # rotate the stream so that a decodable message straddles the cut at sample 25000
+    whole = oracle_mod.Oracle().demod_iq_carry(stream)
+    stream = np.ascontiguousarray(np.roll(stream, -((whole[12]["j"] - 326 + 100) - 25000), axis=0))
+    cuts = [0, 25000, 50000, 75000, 100000]
+    o = oracle_mod.Oracle()
+    ref = []
+    for b in range(4):
+        for f in o.demod_iq_carry(stream[cuts[b]:cuts[b + 1]]):
+            f["buffer"] = b
+            ref.append(f)
+    c = pkg.Context(0)
+    c.set_option(_ffi.OPT_CARRY, 1)
+    got = []
+    for b in range(4):                                   # four calls
+        for f in c.demod_iq(stream[cuts[b]:cuts[b + 1]]):
+            f["buffer"] = b
+            got.append(f)
+    assert frames_key(got) == frames_key(ref)
+    c.icao_flush()
+    c.set_option(_ffi.OPT_CARRY, 1)                      # restart continuity
+    batch = np.ascontiguousarray(stream.reshape(4, 25000, 2))
+    assert frames_key(c.demod_iq_batch(batch, 4, 25000)) == frames_key(ref)   # one batched call
+    # cut somewhere else: same frames at the same stream positions
+    c.icao_flush()
+    c.set_option(_ffi.OPT_CARRY, 1)
+    pos = lambda fr, starts: [(starts[f["buffer"]] + f["j"], f["msg"].hex()) for f in fr]
+    cuts2 = [0, 10123, 10500, 60001, 100000]
+    got2 = []
+    for b in range(4):
+        for f in c.demod_iq(stream[cuts2[b]:cuts2[b + 1]]):
+            f["buffer"] = b
+            got2.append(f)
+    assert pos(got2, cuts2) == pos(ref, cuts)
+    # and more than the reference semantics find
+    c.set_option(_ffi.OPT_CARRY, 0)
+    c.icao_flush()
+    assert len(c.demod_iq_batch(batch, 4, 25000)) < len(ref)
+    c.close()

@@ -108,3 +108,29 @@ def test_two_pass_equals_sequential(captures, oracle_mod):
     for g, s in zip(got, seq):
         assert g == [(f["j"], f["phase"], f["score"], len(f["msg"])) for f in s]
     assert members == os_.members()
+
+
+def test_carry_mode_split_invariance(oracle_mod):
+    """Stream continuity (the checker of B200ADSB_OPT_CARRY): cutting a stream into buffers at
+    arbitrary points does not change what is decoded, and it recovers frames that the
+    reference's zero-filled leading slots lose at buffer boundaries."""
+    from dump1090_rs_b200 import synth
+    stream, inj = synth.make_buffer(31, 0, n=100000, msgs_per_buffer=90, icao_pool=5)
+    whole = oracle_mod.Oracle().demod_iq_carry(stream)
+    ref_stream = [(f["j"] - 326, f["phase"], f["score"], f["msg"]) for f in whole]
+    # cuts in the middle of decodable messages, and elsewhere
+    mid = [f[0] + 100 for f in ref_stream[5:45:13]]
+    assert len(mid) == 4 and mid == sorted(mid)
+    for cuts in (mid[:3], [400, 10123, 10500, 60001], [33333, 66666]):
+        o = oracle_mod.Oracle()
+        got, start = [], 0
+        for end in cuts + [len(stream)]:
+            for f in o.demod_iq_carry(stream[start:end]):
+                got.append((start + f["j"] - 326, f["phase"], f["score"], f["msg"]))
+            start = end
+        assert got == ref_stream, cuts
+    # the reference semantics (no carry) lose frames at the cuts
+    o = oracle_mod.Oracle()
+    edges = [0] + mid[:3] + [len(stream)]
+    plain = sum(len(o.demod_iq(stream[a:b])) for a, b in zip(edges[:-1], edges[1:]))
+    assert plain < len(ref_stream)
