@@ -421,76 +421,93 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     if (!q.active)
         return B200ADSB_ERR_STATE;
     prof_begin(c, c->other_events);
-    events_finalize_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
-                                                      c->d_ev_tmp, c->d_new_keys, c->d_counters,
-                                                      c->d_members, kEvSlots - 1, c->d_bloom);
-    CK(c, cudaGetLastError());
     const uint32_t n_ctas = (q.n_tiles + 31) / 32;
-    if (q.n_tiles) {
-        ResolveParams rp{};
-        rp.rec = c->d_rec;
-        rp.tile_dir = c->d_tile_dir;
-        rp.n_tiles = q.n_tiles;
-        rp.tiles_per_buffer = q.tpb;
-        rp.emit_info = c->d_emit_info;
-        rp.tile_emit = c->d_tile_emit;
-        rp.cta_sum = c->d_cta_sum;
-        rp.bloom = c->d_bloom;
-        rp.rec_score = q.msgs ? c->d_rec_score : nullptr;   // only the message-level API reads scores
-        rp.members = c->d_members;
-        rp.ev_keys = c->d_ev_keys;
-        rp.ev_ord = c->d_ev_ord;
-        rp.ev_mask = kEvSlots - 1;
-        rp.ord_first = q.ord_first;
-        rp.ord_stride = q.ord_stride;
-        resolve_kernel<<<n_ctas, kResolveThreads, 0, c->stream>>>(rp);
-        CK(c, cudaGetLastError());
-    }
-    // exclusive scan over the per-block sums (32 tiles each); total -> counters[C_FRAMES]
-    tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_cta_sum, n_ctas, c->d_counters);
-    CK(c, cudaGetLastError());
-    if (d_per_buffer_counts && q.n_buffers) {
-        buffer_counts_kernel<<<(q.n_buffers + 255) / 256, 256, 0, c->stream>>>(
-            c->d_tile_emit, q.n_buffers, q.tpb, d_per_buffer_counts);
-        CK(c, cudaGetLastError());
-        c->timing.other_launches++;
-    }
-    if (q.n_tiles) {
-        EmitParams ep{};
-        ep.in = q.in;
-        ep.lengths = q.lengths;
-        ep.spb = q.spb;
-        ep.stride = q.stride;
-        ep.rec = c->d_rec;
-        ep.tile_dir = c->d_tile_dir;
-        ep.emit_info = c->d_emit_info;
-        ep.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
-        ep.tail = c->d_tail[c->tail_cur];
-        ep.tile_cnt = c->d_tile_emit;
-        ep.cta_excl = c->d_cta_sum;
-        ep.n_tiles = q.n_tiles;
-        ep.tiles_per_buffer = q.tpb;
-        ep.out = d_out;
-        ep.cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
-        ep.msgs = q.msgs;
-        if (q.from_mag)
-            emit_kernel<true><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
-        else
-            emit_kernel<false><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
-        CK(c, cudaGetLastError());
-    }
+    FinalizeArgs fa{c->d_ev_keys, c->d_ev_ord, c->d_ev_used, c->d_ev_tmp, c->d_new_keys, c->d_counters,
+                    c->d_members, kEvSlots - 1, c->d_bloom};
+    ResolveParams rp{};
+    rp.rec = c->d_rec;
+    rp.tile_dir = c->d_tile_dir;
+    rp.n_tiles = q.n_tiles;
+    rp.tiles_per_buffer = std::max(q.tpb, 1);
+    rp.emit_info = c->d_emit_info;
+    rp.tile_emit = c->d_tile_emit;
+    rp.cta_sum = c->d_cta_sum;
+    rp.bloom = c->d_bloom;
+    rp.rec_score = q.msgs ? c->d_rec_score : nullptr;   // only the message-level API reads scores
+    rp.members = c->d_members;
+    rp.ev_keys = c->d_ev_keys;
+    rp.ev_ord = c->d_ev_ord;
+    rp.ev_mask = kEvSlots - 1;
+    rp.ord_first = q.ord_first;
+    rp.ord_stride = q.ord_stride;
+    EmitParams ep{};
+    ep.in = q.in;
+    ep.lengths = q.lengths;
+    ep.spb = q.spb;
+    ep.stride = q.stride;
+    ep.rec = c->d_rec;
+    ep.tile_dir = c->d_tile_dir;
+    ep.emit_info = c->d_emit_info;
+    ep.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
+    ep.tail = c->d_tail[c->tail_cur];
+    ep.tile_cnt = c->d_tile_emit;
+    ep.cta_excl = c->d_cta_sum;
+    ep.n_tiles = q.n_tiles;
+    ep.tiles_per_buffer = std::max(q.tpb, 1);
+    ep.out = d_out;
+    ep.cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
+    ep.msgs = q.msgs;
     const bool save_tail = c->carry && !q.from_mag && !q.msgs && q.n_buffers > 0;
-    if (save_tail) {
-        save_tail_kernel<<<1, 352, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride, q.lengths,
-                                                   q.spb, q.n_buffers, c->d_tail[c->tail_cur],
-                                                   c->d_tail[c->tail_cur ^ 1]);
+    const bool small = n_ctas <= 16 && !d_per_buffer_counts;
+    if (small) {
+        // one launch for the whole second stage (the tail is saved first: commit ends the kernel)
+        if (save_tail) {
+            save_tail_kernel<<<1, 352, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride, q.lengths,
+                                                       q.spb, q.n_buffers, c->d_tail[c->tail_cur],
+                                                       c->d_tail[c->tail_cur ^ 1]);
+            CK(c, cudaGetLastError());
+        }
+        if (q.from_mag)
+            resolve_small_kernel<true><<<1, kResolveThreads, 0, c->stream>>>(fa, rp, ep, n_ctas);
+        else
+            resolve_small_kernel<false><<<1, kResolveThreads, 0, c->stream>>>(fa, rp, ep, n_ctas);
         CK(c, cudaGetLastError());
+        c->timing.other_launches += 1 + (save_tail ? 1 : 0);
+    } else {
+        events_finalize_kernel<<<1, 1024, 0, c->stream>>>(fa);
+        CK(c, cudaGetLastError());
+        if (q.n_tiles) {
+            resolve_kernel<<<n_ctas, kResolveThreads, 0, c->stream>>>(rp);
+            CK(c, cudaGetLastError());
+        }
+        // exclusive scan over the per-block sums (32 tiles each); total -> counters[C_FRAMES]
+        tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_cta_sum, n_ctas, c->d_counters);
+        CK(c, cudaGetLastError());
+        if (d_per_buffer_counts && q.n_buffers) {
+            buffer_counts_kernel<<<(q.n_buffers + 255) / 256, 256, 0, c->stream>>>(
+                c->d_tile_emit, q.n_buffers, q.tpb, d_per_buffer_counts);
+            CK(c, cudaGetLastError());
+            c->timing.other_launches++;
+        }
+        if (q.n_tiles) {
+            if (q.from_mag)
+                emit_kernel<true><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
+            else
+                emit_kernel<false><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
+            CK(c, cudaGetLastError());
+        }
+        if (save_tail) {
+            save_tail_kernel<<<1, 352, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride, q.lengths,
+                                                       q.spb, q.n_buffers, c->d_tail[c->tail_cur],
+                                                       c->d_tail[c->tail_cur ^ 1]);
+            CK(c, cudaGetLastError());
+        }
+        events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
+                                                        c->d_new_keys, c->d_counters, c->d_members);
+        CK(c, cudaGetLastError());
+        c->timing.other_launches += 5;
     }
-    events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
-                                                    c->d_new_keys, c->d_counters, c->d_members);
-    CK(c, cudaGetLastError());
     prof_end(c, c->other_events);
-    c->timing.other_launches += 5;
     int rc = read_counters(c);
     if (rc) { q.active = false; return rc; }
     if (c->h_counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF))

@@ -1096,7 +1096,15 @@ __global__ void events_import_kernel(const unsigned long long *pairs, uint32_t n
 
 // Capacity rule of icao_filter_add (src/icao_filter.rs:46-62): the table holds the
 // first 4096 distinct keys by first-add order; later ones are dropped.  One block.
-__global__ void __launch_bounds__(1024) events_finalize_kernel(
+struct FinalizeArgs {
+    uint32_t *ev_keys;
+    unsigned long long *ev_ord;
+    const uint32_t *ev_used;
+    uint32_t *ev_tmp, *new_keys, *counters, *members;
+    uint32_t ev_mask;
+    uint32_t *bloom;
+};
+__device__ __forceinline__ void events_finalize_body(
     const uint32_t *ev_keys, unsigned long long *ev_ord, const uint32_t *ev_used, uint32_t *ev_tmp,
     uint32_t *new_keys, uint32_t *counters, const uint32_t *members, uint32_t ev_mask, uint32_t *bloom)
 {
@@ -1163,10 +1171,16 @@ __global__ void __launch_bounds__(1024) events_finalize_kernel(
     }
 }
 
+__global__ void __launch_bounds__(1024) events_finalize_kernel(const FinalizeArgs a)
+{
+    events_finalize_body(a.ev_keys, a.ev_ord, a.ev_used, a.ev_tmp, a.new_keys, a.counters, a.members, a.ev_mask,
+                         a.bloom);
+}
+
 // after resolve: the admitted keys join the filter; the event table is recycled
-__global__ void __launch_bounds__(1024) events_commit_kernel(
-    uint32_t *ev_keys, unsigned long long *ev_ord, const uint32_t *ev_used, const uint32_t *new_keys,
-    uint32_t *counters, uint32_t *members)
+__device__ __forceinline__ void events_commit_body(uint32_t *ev_keys, unsigned long long *ev_ord,
+                                                   const uint32_t *ev_used, const uint32_t *new_keys,
+                                                   uint32_t *counters, uint32_t *members)
 {
     // a scan that overflowed the candidate pool or the event table is redone by the host:
     // nothing of it may reach the filter
@@ -1186,6 +1200,12 @@ __global__ void __launch_bounds__(1024) events_commit_kernel(
         counters[C_ADMIT] = 0;
         counters[C_NEWCNT] = 0;
     }
+}
+__global__ void __launch_bounds__(1024) events_commit_kernel(uint32_t *ev_keys, unsigned long long *ev_ord,
+                                                             const uint32_t *ev_used, const uint32_t *new_keys,
+                                                             uint32_t *counters, uint32_t *members)
+{
+    events_commit_body(ev_keys, ev_ord, ev_used, new_keys, counters, members);
 }
 
 // ================================================================== resolve
@@ -1219,11 +1239,11 @@ __device__ __forceinline__ bool is_member(const ResolveParams &p, uint32_t key, 
 
 // one warp per tile, 32 tiles per block; lanes stride over the tile's records
 constexpr int kResolveThreads = 1024;
-__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const ResolveParams p)
+__device__ __forceinline__ void resolve_body(const ResolveParams &p, const uint32_t blk)
 {
     __shared__ uint32_t s_cnt[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile = blockIdx.x * 32 + warp;
+    const uint32_t tile = blk * 32 + warp;
     uint32_t emitted = 0;
     if (tile < p.n_tiles) {
         const uint2 d = p.tile_dir[tile];
@@ -1281,14 +1301,18 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const ResolveP
         for (int o = 16; o; o >>= 1)
             v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0)
-            p.cta_sum[blockIdx.x] = v;
+            p.cta_sum[blk] = v;
     }
+    __syncthreads();   // s_cnt is reused by the next block of tiles in the fused small-batch kernel
+}
+__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const ResolveParams p)
+{
+    resolve_body(p, blockIdx.x);
 }
 
 // exclusive scan of tile_emit (in place) by one block; total -> counters[C_FRAMES];
 // per-buffer counts optional
-__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t *tile_emit, uint32_t n_tiles,
-                                                         uint32_t *counters)
+__device__ __forceinline__ void tile_scan_body(uint32_t *tile_emit, uint32_t n_tiles, uint32_t *counters)
 {
     __shared__ uint32_t s_w[32];
     __shared__ uint32_t s_carry;
@@ -1332,6 +1356,10 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t *tile_emit, ui
     if (threadIdx.x == 0)
         counters[C_FRAMES] = s_carry;
 }
+__global__ void __launch_bounds__(1024) tile_scan_kernel(uint32_t *tile_emit, uint32_t n_tiles, uint32_t *counters)
+{
+    tile_scan_body(tile_emit, n_tiles, counters);
+}
 
 __global__ void buffer_counts_kernel(const uint32_t *tile_cnt, uint32_t n_buffers, int tpb, uint32_t *out)
 {
@@ -1368,13 +1396,13 @@ struct EmitParams {
 // (src/demod_2400.rs:158-182 in closed form: bit n of try_phase t is decided at
 //  P = 5(j+19)+t+12n, sample P/5, correlator P%5)
 template <bool FROM_MAG>
-__global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams p)
+__device__ __forceinline__ void emit_body(const EmitParams &p, const uint32_t blk)
 {
     __shared__ uint16_t s_mag[32][288];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t tile = blockIdx.x * 32 + warp;
+    const uint32_t tile = blk * 32 + warp;
     // this tile's first output slot: block prefix + the counts of the block's earlier tiles
-    const uint32_t t_l = blockIdx.x * 32 + (uint32_t)lane;
+    const uint32_t t_l = blk * 32 + (uint32_t)lane;
     const uint32_t c_l = t_l < p.n_tiles ? p.tile_cnt[t_l] : 0u;
     uint32_t incl = c_l;
 #pragma unroll
@@ -1384,7 +1412,7 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
             incl += t;
     }
     const uint32_t my_cnt = __shfl_sync(0xffffffffu, c_l, warp);
-    uint32_t out_idx = p.cta_excl[blockIdx.x] + __shfl_sync(0xffffffffu, incl - c_l, warp);
+    uint32_t out_idx = p.cta_excl[blk] + __shfl_sync(0xffffffffu, incl - c_l, warp);
     if (tile >= p.n_tiles || my_cnt == 0u)
         return;
     const uint2 d = p.tile_dir[tile];
@@ -1472,6 +1500,34 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
             out_idx++;
         }
     }
+}
+
+template <bool FROM_MAG>
+__global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams p)
+{
+    emit_body<FROM_MAG>(p, blockIdx.x);
+}
+
+// Small batches (one SDR read per call): the whole second stage in one launch of one block --
+// finalise, resolve, scan, emit, commit -- because five dependent launches of a few
+// microseconds each would dominate the call.
+template <bool FROM_MAG>
+__global__ void __launch_bounds__(kResolveThreads) resolve_small_kernel(const FinalizeArgs fa, const ResolveParams rp,
+                                                                        const EmitParams ep, const uint32_t n_ctas)
+{
+    events_finalize_body(fa.ev_keys, fa.ev_ord, fa.ev_used, fa.ev_tmp, fa.new_keys, fa.counters, fa.members,
+                         fa.ev_mask, fa.bloom);
+    __syncthreads();
+    for (uint32_t blk = 0; blk < n_ctas; blk++)
+        resolve_body(rp, blk);
+    __syncthreads();
+    tile_scan_body(rp.cta_sum, n_ctas, fa.counters);
+    __syncthreads();
+    for (uint32_t blk = 0; blk < n_ctas; blk++) {
+        emit_body<FROM_MAG>(ep, blk);
+        __syncthreads();
+    }
+    events_commit_body(fa.ev_keys, fa.ev_ord, fa.ev_used, fa.new_keys, fa.counters, fa.members);
 }
 
 // carry mode: the last 326 samples of the stream (walking back over this batch's buffers,
