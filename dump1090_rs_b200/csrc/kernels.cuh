@@ -216,6 +216,47 @@ __device__ __forceinline__ u64x f2_add_rz(u64x a, u64x b)
     asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+#ifndef B200_MAG_V2
+#define B200_MAG_V2 1
+#endif
+#if B200_MAG_V2
+// v2: I2F.S16 straight from the halves of the IQ word (no XOR/PRMT/rescale), everything kept
+// scaled by 2^15 (powers of two commute with every rounding here, nothing over/underflows:
+// x' = x * 2^30 <= 2^31), residual with the negated operand folded into FFMA2:
+//   s0 = x*y, e = fma(-s0, s0, x), s = fma(e, y/2, s0)   (same reals, same roundings as v1)
+__device__ __forceinline__ float cvt_s16_lo(uint32_t w)
+{
+    float f;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %1; cvt.rn.f32.s16 %0, l; }" : "=f"(f) : "r"(w));
+    return f;
+}
+__device__ __forceinline__ float cvt_s16_hi(uint32_t w)
+{
+    float f;
+    asm("{ .reg .b16 l, h; mov.b32 {l, h}, %1; cvt.rn.f32.s16 %0, h; }" : "=f"(f) : "r"(w));
+    return f;
+}
+__device__ __forceinline__ u64x mag_pair_fast2(uint32_t wa, uint32_t wb)
+{
+    const u64x fq = f2_pack(cvt_s16_lo(wa), cvt_s16_lo(wb));
+    const u64x fi = f2_pack(cvt_s16_hi(wa), cvt_s16_hi(wb));
+    const u64x x = f2_fma(fi, fi, f2_mul(fq, fq));
+    float xa, xb, ya, yb;
+    f2_unpack(f2_add(x, f2_pack(1e-20f, 1e-20f)), xa, xb);
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ya) : "f"(xa));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(yb) : "f"(xb));
+    const u64x y = f2_pack(ya, yb);
+    const u64x s0 = f2_mul(x, y);
+    const u64x yh = f2_mul(y, f2_pack(0.5f, 0.5f));
+    float s0a, s0b;
+    f2_unpack(s0, s0a, s0b);
+    const u64x e = f2_fma(f2_pack(-s0a, -s0b), s0, x);          // x - s0^2, one rounding
+    const u64x s = f2_fma(e, yh, s0);
+    float va, vb;
+    f2_unpack(f2_fma(s, f2_pack(0x1.fffep0f, 0x1.fffep0f), f2_pack(0.5f, 0.5f)), va, vb);   // 65535 * 2^-15
+    return f2_add_rz(f2_pack(fminf(va, 65535.0f), fminf(vb, 65535.0f)), f2_pack(8388608.0f, 8388608.0f));
+}
+#else
 __device__ __forceinline__ u64x mag_pair_fast2(uint32_t wa, uint32_t wb)
 {
     const uint32_t ta = wa ^ 0x80008000u, tb = wb ^ 0x80008000u;
@@ -240,6 +281,7 @@ __device__ __forceinline__ u64x mag_pair_fast2(uint32_t wa, uint32_t wb)
     f2_unpack(f2_fma(s, f2_pack(65535.0f, 65535.0f), f2_pack(0.5f, 0.5f)), va, vb);
     return f2_add_rz(f2_pack(fminf(va, 65535.0f), fminf(vb, 65535.0f)), f2_pack(8388608.0f, 8388608.0f));
 }
+#endif
 __device__ __forceinline__ uint32_t mag_bits_fast(uint32_t w)
 {
     float a, b;
