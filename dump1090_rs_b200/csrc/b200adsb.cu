@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "scan7.cuh"
 
 using namespace b200;
 
@@ -55,7 +56,8 @@ struct b200adsb_ctx {
     unsigned long long *d_ev_ord = nullptr;
     uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr, *d_lut = nullptr;
     uint32_t h_lut[kLutWords];
-    int lut_T = 0;
+    int lut_T = 0, lut_WP = 0;
+    int scan_ver = 7;   // stage-1 kernel generation (B200ADSB_SCAN=6 selects the previous one for A/B runs)
     uint32_t *d_scalar = nullptr;
 
     uint32_t *d_rec = nullptr, *d_emit_info = nullptr;
@@ -286,7 +288,9 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.ord_stride = q.ord_stride;
     p.crc_tabs = c->d_crc_tabs;
     ScanSmem L(q.T);
-    if (c->lut_T != q.T) {
+    Scan7Smem L7(q.T);
+    const int WPsel = c->scan_ver >= 7 ? L7.WP : L.WP;
+    if (c->lut_T != q.T || c->lut_WP != WPsel) {
         // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
         // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream in
         // plane[phi][rho][WP], and whether the stream index q = A/12 advances by one
@@ -295,11 +299,12 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
             const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
             const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
             const int rr = ra + e5 + zd, wrap = rr >= 12 ? 1 : 0;
-            c->h_lut[i] = (uint32_t)((phi * 12 + rr - 12 * wrap) * L.WP) | ((uint32_t)wrap << 16);
+            c->h_lut[i] = (uint32_t)((phi * 12 + rr - 12 * wrap) * WPsel) | ((uint32_t)wrap << 16);
         }
         CK(c, cudaStreamSynchronize(c->stream));   // a previous launch may still read the table
         CK(c, cudaMemcpyAsync(c->d_lut, c->h_lut, sizeof c->h_lut, cudaMemcpyHostToDevice, c->stream));
         c->lut_T = q.T;
+        c->lut_WP = WPsel;
     }
     p.lut = c->d_lut;
     p.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
@@ -319,7 +324,30 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     if (grid == 0)
         return B200ADSB_OK;
     prof_begin(c, c->scan_events);
-    if (q.from_mag) {
+    if (c->scan_ver >= 7) {
+        Scan7Params P7;
+        P7.s = p;
+        P7.off_planes = (uint32_t)L7.off_planes;
+        P7.off_surv = (uint32_t)L7.off_surv;
+        P7.off_masks = (uint32_t)L7.off_masks;
+        P7.off_list = (uint32_t)L7.off_list;
+        P7.off_cand = (uint32_t)L7.off_cand;
+        P7.NG = L7.NG;
+        P7.WP = L7.WP;
+        P7.nw = L7.nw;
+        size_t bytes7 = L7.bytes;
+        if (const char *ex = getenv("B200ADSB_DEBUG_EXTRA_SMEM"))
+            bytes7 += (size_t)atoi(ex);
+        if (q.from_mag) {
+            CK(c, cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes7));
+            CK(c, cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            scan7_kernel<true><<<grid, k7Threads, bytes7, c->stream>>>(P7);
+        } else {
+            CK(c, cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes7));
+            CK(c, cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            scan7_kernel<false><<<grid, k7Threads, bytes7, c->stream>>>(P7);
+        }
+    } else if (q.from_mag) {
         CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
         CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         scan_kernel<true><<<grid, kThreads, L.bytes, c->stream>>>(p);
@@ -603,6 +631,8 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
             return fail(B200ADSB_ERR_CUDA); \
     } while (0)
     CKC(cudaSetDevice(device));
+    if (const char *sv = getenv("B200ADSB_SCAN"))
+        c->scan_ver = atoi(sv) == 6 ? 6 : 7;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {

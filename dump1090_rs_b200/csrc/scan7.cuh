@@ -1,0 +1,575 @@
+// dump1090_rs_b200/csrc/scan7.cuh -- scan kernel v7 (sm_100a): the same stage-1 contract as
+// scan_kernel in kernels.cuh (one thread block per tile -> 24-byte records + ICAO add-events),
+// reorganised so that magnitudes, first differences, correlator signs and edge bits never
+// leave registers between the IQ load and the bit planes.
+//
+// Dense phase.  The halo-extended tile is NG groups of 192 samples.  Three lanes own a group:
+// lane c (0..2) takes, for slot k = 15..0, the four consecutive samples 192G + 12k + 4c + e
+// (one LDG.128 of IQ).  Residue rho = 4c + e of the 12-sample Mode-S bit period is therefore
+// fixed per (lane, e) and slot k is bit k of a 16-bit accumulator: after 16 slots every
+// accumulator IS one halfword of the mod-12 de-interleaved plane[phi][rho] (bit q <-> tile
+// magnitude index 12q + rho), stored with one STS.U16.  The three magnitudes to the right of
+// a row come from lane+1 (c < 2) or from lane-2's previous slot (c == 2) by shuffle.
+// Samples are paired (e, e+2) in the packed f32x2 pipe: the pairs (d0,d2) (d1,d3) (d2,d4)
+// (d3,d5) of first differences serve both correlator pairs without register moves.
+//   src/utils.rs:43-58 (magnitude), src/demod_2400.rs:62-83 (correlators), :221-317 (edges)
+//
+// Sparse phases.
+//   P3a  one warp, lane = word column, residue static: the five templates as AND of the
+//        rising/falling planes (32 positions at stride 12 per word) -> one match mask per
+//        (template case, rho, word)
+//   P3b  block-wide ordered compaction of the masks into a case-sorted list, then the SNR and
+//        quiet-zone gates one match per thread                       (src/demod_2400.rs:129-146)
+//   P4   as in v6: field extraction from the planes, class-staged CRC-24, records, add-events
+#pragma once
+#include "kernels.cuh"
+
+namespace b200 {
+
+constexpr int k7Threads = 128;
+constexpr int k7Warps = k7Threads / 32;
+constexpr int k7Slots = 16;
+constexpr int k7Group = 12 * k7Slots;       // 192 samples
+constexpr int k7GroupsPerWarp = 10;         // 30 of 32 lanes
+constexpr int k7GroupsPerPass = k7GroupsPerWarp * k7Warps;
+constexpr int k7CandCap = 128;              // survivors decoded per window
+constexpr int k7FieldItems = 5 * k7CandCap;
+constexpr int k7ListCap = 1024;             // template matches gated per round
+#ifndef B200_SCAN7_MIN_BLOCKS
+#define B200_SCAN7_MIN_BLOCKS 6
+#endif
+
+// shared memory plan for tile size T
+struct Scan7Smem {
+    int NG, WP, nw, mag_len;
+    size_t off_planes, off_surv, off_masks, off_list, off_cand, bytes;
+    __host__ __device__ explicit Scan7Smem(int T)
+    {
+        NG = (T + kHaloTot + k7Group - 1) / k7Group;
+        mag_len = NG * k7Group + 32;                  // + pad read by gates of halo positions
+        WP = (NG + 1) / 2 + 1;                        // words per plane row (+1 read by funnel shifts)
+        nw = (T + 31) / 32;
+        size_t o = (size_t)mag_len * 2;
+        if (o < (size_t)k7FieldItems * 5 * 4)         // P4 field staging aliases the (dead) magnitudes
+            o = (size_t)k7FieldItems * 5 * 4;
+        o = (o + 15) & ~(size_t)15;
+        off_planes = o;                               // [7][12][WP]: 5 correlators, rising, falling
+        o += (size_t)7 * 12 * WP * 4;
+        off_surv = o;
+        o += (size_t)nw * 4;
+        o = (o + 15) & ~(size_t)15;
+        off_masks = o;                                // [5][12][WP] template match masks
+        o += (size_t)5 * 12 * WP * 4;
+        off_list = o;
+        o += (size_t)k7ListCap * 2;
+        off_cand = o;
+        o += (size_t)k7CandCap * 2;
+        bytes = (o + 15) & ~(size_t)15;
+    }
+};
+
+struct Scan7Params {
+    ScanParams s;
+    uint32_t off_planes, off_surv, off_masks, off_list, off_cand;
+    int NG, WP, nw;
+};
+
+// one row of four consecutive magnitudes, as f32 bit patterns 2^23 + m, paired (m0,m2) (m1,m3)
+struct Row {
+    u64x q0, q1;
+};
+
+template <bool FROM_MAG>
+__device__ __forceinline__ Row row_slow(const ScanParams &p, const uint32_t *b32, const uint16_t *d16, int s,
+                                        int i, int len, const uint32_t *prev, int prev_len)
+{
+    Row r;
+    if (!FROM_MAG) {
+        uint32_t w[4];
+        if (s >= 0 && s + 3 < len && p.vec_ok) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(b32 + s));
+            w[0] = (uint32_t)v.x; w[1] = (uint32_t)v.y; w[2] = (uint32_t)v.z; w[3] = (uint32_t)v.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                w[e] = iq_word(b32, s + e, len, prev, prev_len);
+        }
+        r.q0 = mag_pair_fast2(w[0], w[2]);
+        r.q1 = mag_pair_fast2(w[1], w[3]);
+    } else {
+        uint32_t m[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const int ia = i + e;
+            m[e] = 0x4B000000u + ((ia >= 0 && ia < kMagLen) ? (uint32_t)__ldg(d16 + ia) : 0u);
+        }
+        r.q0 = f2_pack(__uint_as_float(m[0]), __uint_as_float(m[2]));
+        r.q1 = f2_pack(__uint_as_float(m[1]), __uint_as_float(m[3]));
+    }
+    return r;
+}
+
+__device__ __forceinline__ uint32_t sgn_in(float x, uint32_t acc)   // acc = acc << 1 | sign(x)
+{
+    return __funnelshift_l(__float_as_uint(x), acc, 1);
+}
+
+// the five PPM correlators of a sample pair on first differences u, v, w
+// (demod_2400.rs:72-83 negated so that "bit = 1" is the sign bit):
+//   5u+2v, 4u+3v, 3u+4v, 2u+5v, u+6v+w      all exact in f32 (|.| < 2^20)
+__device__ __forceinline__ void corr_pair(u64x u, u64x v, u64x w, uint32_t *lo, uint32_t *hi)
+{
+    const u64x five = f2_pack(5.0f, 5.0f);
+    const u64x g = f2_sub(v, u);
+    const u64x x0 = f2_fma(u, five, f2_add(v, v));
+    const u64x x1 = f2_add(x0, g), x2 = f2_add(x1, g), x3 = f2_add(x2, g);
+    const u64x x4 = f2_add(f2_add(x3, g), w);
+    float a, b;
+    f2_unpack(x0, a, b); lo[0] = sgn_in(a, lo[0]); hi[0] = sgn_in(b, hi[0]);
+    f2_unpack(x1, a, b); lo[1] = sgn_in(a, lo[1]); hi[1] = sgn_in(b, hi[1]);
+    f2_unpack(x2, a, b); lo[2] = sgn_in(a, lo[2]); hi[2] = sgn_in(b, hi[2]);
+    f2_unpack(x3, a, b); lo[3] = sgn_in(a, lo[3]); hi[3] = sgn_in(b, hi[3]);
+    f2_unpack(x4, a, b); lo[4] = sgn_in(a, lo[4]); hi[4] = sgn_in(b, hi[4]);
+}
+
+struct DenseState {
+    uint32_t acc[4][7];      // [e][plane]: planes 0..4 correlators, 5 rising, 6 falling
+    float pm0, pm1, pm2;     // first three magnitudes of the row 12 samples to the right (c == 0 lanes)
+};
+
+// one slot: row r -> magnitudes to shared memory, 28 sign bits into the accumulators
+__device__ __forceinline__ void dense_slot(DenseState &st, const Row r, bool is_c0, int src_lane, uint16_t *mag_row,
+                                           bool store)
+{
+    float m0, m1, m2, m3;
+    f2_unpack(r.q0, m0, m2);
+    f2_unpack(r.q1, m1, m3);
+    // right neighbours m4..m6: lane+1's m0..m2 of this slot, or (c == 2) lane-2's m0..m2 of the
+    // previous slot = the row 12 samples further
+    const float t0 = is_c0 ? st.pm0 : m0, t1 = is_c0 ? st.pm1 : m1, t2 = is_c0 ? st.pm2 : m2;
+    const float m4 = __shfl_sync(0xffffffffu, t0, src_lane);
+    const float m5 = __shfl_sync(0xffffffffu, t1, src_lane);
+    const float m6 = __shfl_sync(0xffffffffu, t2, src_lane);
+    st.pm0 = m0; st.pm1 = m1; st.pm2 = m2;
+    const u64x q2 = f2_pack(m2, m4), q3 = f2_pack(m3, m5), q4 = f2_pack(m4, m6);
+    const u64x p0 = f2_sub(r.q1, r.q0), p1 = f2_sub(q2, r.q1), p2 = f2_sub(q3, q2), p3 = f2_sub(q4, q3);
+    const u64x n0 = f2_sub(r.q0, r.q1), n1 = f2_sub(r.q1, q2);
+    float a, b;
+    f2_unpack(p0, a, b); st.acc[0][6] = sgn_in(a, st.acc[0][6]); st.acc[2][6] = sgn_in(b, st.acc[2][6]);   // falling
+    f2_unpack(p1, a, b); st.acc[1][6] = sgn_in(a, st.acc[1][6]); st.acc[3][6] = sgn_in(b, st.acc[3][6]);
+    f2_unpack(n0, a, b); st.acc[0][5] = sgn_in(a, st.acc[0][5]); st.acc[2][5] = sgn_in(b, st.acc[2][5]);   // rising
+    f2_unpack(n1, a, b); st.acc[1][5] = sgn_in(a, st.acc[1][5]); st.acc[3][5] = sgn_in(b, st.acc[3][5]);
+    corr_pair(p0, p1, p2, st.acc[0], st.acc[2]);
+    corr_pair(p1, p2, p3, st.acc[1], st.acc[3]);
+    if (store)
+        *reinterpret_cast<uint2 *>(mag_row) =
+            make_uint2(__byte_perm(__float_as_uint(m0), __float_as_uint(m1), 0x5410),
+                       __byte_perm(__float_as_uint(m2), __float_as_uint(m3), 0x5410));
+}
+
+__device__ __forceinline__ void gate_eval7(const uint16_t *mag, uint32_t *surv, int mi, uint32_t cs, int npos)
+{
+    const int jl = mi - kHaloFront;
+    if (jl < 0 || jl >= npos)
+        return;
+    gate_eval(mag, surv, mi, cs);
+}
+
+template <bool FROM_MAG>
+__global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel(const Scan7Params P)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const ScanParams &p = P.s;
+    uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
+    uint32_t *fb = reinterpret_cast<uint32_t *>(smem);                      // P4: staged fields (mag is dead)
+    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + P.off_planes);   // [7][12][WP]
+    uint32_t *surv = reinterpret_cast<uint32_t *>(smem + P.off_surv);
+    uint32_t *masks = reinterpret_cast<uint32_t *>(smem + P.off_masks);     // [5][12][WP]
+    uint16_t *list = reinterpret_cast<uint16_t *>(smem + P.off_list);
+    uint16_t *cand = reinterpret_cast<uint16_t *>(smem + P.off_cand);
+    const uint32_t *tabs = p.crc_tabs;
+    const uint32_t *lut = p.lut;
+    __shared__ uint32_t s_warp_tot[k7Warps];
+    __shared__ uint32_t s_base, s_count, s_ok, s_nlong, s_nshort;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
+    const int kt = (int)(tile - b * (uint32_t)p.tiles_per_buffer);
+    const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
+    const int tile_start = kt * p.T;
+    if (tile_start >= len) {
+        if (tid == 0)
+            p.tile_dir[tile] = make_uint2(0u, 0u);
+        return;
+    }
+    const int npos = min(p.T, len - tile_start);
+    const int NG = (npos + kHaloTot + k7Group - 1) / k7Group;   // groups actually needed
+    const int WP = P.WP;
+    const int nwq = (NG + 1) / 2;                                // plane words that carry data
+
+    for (int i = tid; i < P.nw; i += k7Threads)
+        surv[i] = 0;
+    for (int i = tid; i < 7 * 12; i += k7Threads) {              // words the dense phase may leave unwritten
+        planes[i * WP + nwq - 1] = 0;
+        planes[i * WP + nwq] = 0;
+    }
+    __syncthreads();
+
+    // ---- P1: dense phase (magnitudes, edges, correlator signs; see the header)
+    {
+        int prev_len = 0;
+        const uint32_t *prev = FROM_MAG ? nullptr
+                                        : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
+        const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
+        const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
+        const int s0 = tile_start - (kTrailing + kHaloFront);    // sample index of tile magnitude 0
+        const int i0 = tile_start - kHaloFront;                   // data index of tile magnitude 0
+        const int gl = lane / 3, c = lane - 3 * gl;
+        const int src_lane = (c < 2) ? min(lane + 1, 31) : lane - 2;
+        const bool is_c0 = c == 0;
+        uint16_t *planes16 = reinterpret_cast<uint16_t *>(planes);
+        for (int gbase = warp * k7GroupsPerWarp; gbase < NG; gbase += k7GroupsPerPass) {
+            const int G = gbase + gl;                              // lanes 30, 31: helpers without stores
+            const bool own = lane < 30 && G < NG;
+            const int r0 = k7Group * G + 4 * c;                    // magnitude index of slot 0
+            DenseState st;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+#pragma unroll
+                for (int f = 0; f < 7; f++)
+                    st.acc[e][f] = 0;
+            // whole warp inside the buffer and 16-byte aligned: plain LDG.128 with one slot of prefetch
+            const int g_lo = k7Group * gbase, g_hi = k7Group * (gbase + k7GroupsPerWarp + 2) + 4;
+            const bool fast = !FROM_MAG && p.vec_ok && s0 + g_lo >= 0 && s0 + g_hi <= len;
+            {
+                const int rb = k7Group * (G + 1);                  // first row of the next group
+                const Row rbnd = row_slow<FROM_MAG>(p, b32, d16, s0 + rb, i0 + rb, len, prev, prev_len);
+                float x, y;
+                f2_unpack(rbnd.q0, st.pm0, st.pm2);
+                f2_unpack(rbnd.q1, st.pm1, y);
+                (void)x;
+            }
+            uint16_t *mrow = mag + r0 + 12 * (k7Slots - 1);
+            if (fast) {
+                // running pointers, two slots per iteration (no register rotation), one pair of prefetch
+                const int4 *src = reinterpret_cast<const int4 *>(b32 + s0 + r0) + 3 * (k7Slots - 1);
+                int4 va = __ldg(src), vb;
+#pragma unroll 1
+                for (int k = k7Slots / 2 - 1; k >= 0; k--) {
+                    vb = __ldg(src - 3);
+                    Row r;
+                    r.q0 = mag_pair_fast2((uint32_t)va.x, (uint32_t)va.z);
+                    r.q1 = mag_pair_fast2((uint32_t)va.y, (uint32_t)va.w);
+                    dense_slot(st, r, is_c0, src_lane, mrow, own);
+                    src -= 6;
+                    if (k > 0)
+                        va = __ldg(src);
+                    r.q0 = mag_pair_fast2((uint32_t)vb.x, (uint32_t)vb.z);
+                    r.q1 = mag_pair_fast2((uint32_t)vb.y, (uint32_t)vb.w);
+                    dense_slot(st, r, is_c0, src_lane, mrow - 12, own);
+                    mrow -= 24;
+                }
+            } else {
+#pragma unroll 1
+                for (int k = k7Slots - 1; k >= 0; k--) {
+                    const int rr = r0 + 12 * k;
+                    const Row r = row_slow<FROM_MAG>(p, b32, d16, s0 + rr, i0 + rr, len, prev, prev_len);
+                    dense_slot(st, r, is_c0, src_lane, mrow, own);
+                    mrow -= 12;
+                }
+            }
+            if (own) {
+                // accumulator (e, f) is halfword G of plane row f*12 + 4c + e
+#pragma unroll
+                for (int f = 0; f < 7; f++)
+#pragma unroll
+                    for (int e = 0; e < 4; e++)
+                        planes16[2 * ((f * 12 + 4 * c + e) * WP) + G] = (uint16_t)st.acc[e][f];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- P3a: preamble templates (demod_2400.rs:221-317).  Warp 0, lane = word column w: the 32
+    // positions 12*(32w+bit)+rho for every residue rho (static).  Edge bit at offset s of such a
+    // position is bit (bit + carry) of row (rho+s) mod 12, carry = (rho+s) / 12.
+    if (warp == 0) {
+        const uint32_t *Rp = planes + 5 * 12 * WP, *Fp = planes + 6 * 12 * WP;
+        for (int w = lane; w < nwq; w += 32) {
+            // sliding windows over t = rho + s: XR[t], XF[t] for t in [rho, rho+12]
+            uint32_t XR[24], XF[24];
+#pragma unroll
+            for (int t = 0; t < 24; t++) {
+                if (t < 12) {
+                    XR[t] = Rp[t * WP + w];
+                    XF[t] = Fp[t * WP + w];
+                } else {
+                    XR[t] = __funnelshift_r(Rp[(t - 12) * WP + w], Rp[(t - 12) * WP + w + 1], 1);
+                    XF[t] = __funnelshift_r(Fp[(t - 12) * WP + w], Fp[(t - 12) * WP + w + 1], 1);
+                }
+            }
+#pragma unroll
+            for (int rho = 0; rho < 12; rho++) {
+#define ER(s) XR[rho + (s)]
+#define EF(s) XF[rho + (s)]
+                const uint32_t quick = ER(0) & EF(12);   // p0 < p1 && p12 > p13 (:221)
+                const uint32_t T3 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(10);
+                const uint32_t T4 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(11);
+                const uint32_t T5 = EF(1) & ER(2) & EF(4) & ER(8) & EF(10) & ER(11);
+                const uint32_t T6 = EF(1) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+                const uint32_t T7 = EF(2) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+#undef ER
+#undef EF
+                // first match wins (:226-317)
+                const uint32_t M0 = quick & T3;
+                const uint32_t M1 = quick & T4 & ~T3;
+                const uint32_t M2 = quick & T5 & ~(T3 | T4);
+                const uint32_t M3 = quick & T6 & ~(T3 | T4 | T5);
+                const uint32_t M4 = quick & T7 & ~(T3 | T4 | T5 | T6);
+                masks[(0 * 12 + rho) * WP + w] = M0;
+                masks[(1 * 12 + rho) * WP + w] = M1;
+                masks[(2 * 12 + rho) * WP + w] = M2;
+                masks[(3 * 12 + rho) * WP + w] = M3;
+                masks[(4 * 12 + rho) * WP + w] = M4;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- P3b: ordered compaction of the match masks (case-major) and the gates
+    {
+        const int nrows = 5 * 12;
+        const int nwords = nrows * nwq;                    // word i <-> (row = i / nwq, w = i % nwq)
+        const int chunk = (nwords + k7Threads - 1) / k7Threads;
+        const int i_lo = min(tid * chunk, nwords), i_hi = min(i_lo + chunk, nwords);
+        int row = i_lo / nwq, w = i_lo - row * nwq;
+        const int row0 = row, w0 = w;
+        int cnt = 0;
+        for (int i = i_lo; i < i_hi; i++) {
+            cnt += __popc(masks[row * WP + w]);
+            if (++w == nwq) {
+                w = 0;
+                row++;
+            }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        if (lane == 31)
+            s_warp_tot[warp] = (uint32_t)incl;
+        __syncthreads();
+        int my_off = incl - cnt, total = 0;
+#pragma unroll
+        for (int wi = 0; wi < k7Warps; wi++) {
+            const int t = (int)s_warp_tot[wi];
+            if (wi < warp)
+                my_off += t;
+            total += t;
+        }
+        for (int base = 0; base < total; base += k7ListCap) {
+            if (cnt && my_off < base + k7ListCap && my_off + cnt > base) {
+                int off = my_off;
+                row = row0;
+                w = w0;
+                for (int i = i_lo; i < i_hi; i++) {
+                    uint32_t m = masks[row * WP + w];
+                    const int cs = row / 12, rho = row - 12 * cs;
+                    while (m) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1;
+                        if (off >= base && off < base + k7ListCap)
+                            list[off - base] = (uint16_t)((12 * (32 * w + bit) + rho) | (cs << 13));
+                        off++;
+                    }
+                    if (++w == nwq) {
+                        w = 0;
+                        row++;
+                    }
+                }
+            }
+            __syncthreads();
+            const int n = min(k7ListCap, total - base);
+            for (int g = tid; g < n; g += k7Threads) {
+                const uint32_t e = list[g];
+                gate_eval7(mag, surv, (int)(e & 0x1fffu), e >> 13, npos);
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+
+    // ---- P4a: count survivors, reserve pool space (positions are emitted in ascending j)
+    const int wi0 = 2 * tid;                                // two survivor words per thread (nw <= 256)
+    const uint32_t wv0 = (wi0 < P.nw) ? surv[wi0] : 0u, wv1 = (wi0 + 1 < P.nw) ? surv[wi0 + 1] : 0u;
+    int my_off;
+    {
+        const int cnt = __popc(wv0) + __popc(wv1);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        __syncthreads();                                     // s_warp_tot reuse
+        if (lane == 31)
+            s_warp_tot[warp] = (uint32_t)incl;
+        __syncthreads();
+        my_off = incl - cnt;
+        uint32_t total = 0;
+#pragma unroll
+        for (int wi = 0; wi < k7Warps; wi++) {
+            const uint32_t t = s_warp_tot[wi];
+            if (wi < warp)
+                my_off += (int)t;
+            total += t;
+        }
+        if (tid == 0) {
+            uint32_t base = 0, ok = 1;
+            if (total) {
+                base = atomicAdd(&p.counters[C_POOL], total);
+                if (base + total > p.pool_cap || base + total < base) {
+                    atomicOr(&p.counters[C_FLAGS], F_POOL_OVF);
+                    ok = 0;
+                }
+                atomicAdd(&p.counters[C_CAND], total);
+            }
+            p.tile_dir[tile] = make_uint2(base, ok ? total : 0u);
+            s_base = base;
+            s_count = total;
+            s_ok = ok;
+            s_nlong = 0;
+            s_nshort = 0;
+        }
+    }
+    __syncthreads();
+    if (!s_ok || s_count == 0)
+        return;
+
+    // ---- P4b: five try-phases per survivor, in windows of k7CandCap survivors (as v6)
+    const int C = (int)s_count;
+    const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
+    for (int win = 0; win < C; win += k7CandCap) {
+        {
+            int off = my_off;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t wv2 = h ? wv1 : wv0;
+                while (wv2) {
+                    const int bit = __ffs(wv2) - 1;
+                    wv2 &= wv2 - 1;
+                    if (off >= win && off < win + k7CandCap)
+                        cand[off - win] = (uint16_t)((wi0 + h) * 32 + bit);
+                    off++;
+                }
+            }
+        }
+        __syncthreads();
+        const int Cw = min(k7CandCap, C - win);
+        uint32_t *rec_w = p.rec + 6ull * (s_base + (uint32_t)win);
+        for (int item = tid; item < 5 * Cw; item += k7Threads) {
+            const int ci = item / 5, tt = item - 5 * ci;
+            const int jl = cand[ci];
+            // demod_2400.rs:158-160: P0 = 5*(mi+19) + try_phase, try_phase = 4+tt
+            const int A = jl + kHaloFront + 19;
+            const int qA = A / 12, rA = A - 12 * qA;
+            const uint32_t *lrow = lut + 25 * rA + 5 * tt;
+            uint32_t f[5];
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const uint32_t e = __ldg(lrow + r);
+                const int q = qA + (int)(e >> 16);
+                const uint32_t *stp = planes + (e & 0xffffu) + (q >> 5);
+                f[r] = __funnelshift_r(stp[0], stp[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
+            }
+            if (tt == 0)
+                rec_w[6 * ci] = (uint32_t)(tile_start + jl);
+            uint32_t wd = 0;
+            int cls = 0;
+            if ((f[0] | f[1] | f[2] | f[3] | f[4]) == 0) {
+                wd = kNoneMarker;                      // all 14 bytes zero -> None (mode_s/mod.rs:51-53)
+            } else {
+                const uint32_t bit = 1u << df_of_fields(f);
+                if (bit & 0xFF370000u)                 // DF 16,17,18,20,21,24..31
+                    cls = 1;
+                else if (bit & 0x00000831u)            // DF 0,4,5,11
+                    cls = 2;
+            }
+            const unsigned act = __activemask();
+            const unsigned ml = __ballot_sync(act, cls == 1), ms = __ballot_sync(act, cls == 2);
+            const int leader = __ffs(act) - 1;
+            uint32_t basel = 0, bases = 0;
+            if (lane == leader) {
+                if (ml)
+                    basel = atomicAdd(&s_nlong, (uint32_t)__popc(ml));
+                if (ms)
+                    bases = atomicAdd(&s_nshort, (uint32_t)__popc(ms));
+            }
+            basel = __shfl_sync(act, basel, leader);
+            bases = __shfl_sync(act, bases, leader);
+            const unsigned lt = (1u << lane) - 1u;
+            if (cls) {
+                const uint32_t slot = cls == 1 ? basel + (uint32_t)__popc(ml & lt)
+                                               : (uint32_t)(k7FieldItems - 1) - (bases + (uint32_t)__popc(ms & lt));
+                uint32_t *o = fb + 5 * slot;
+                o[0] = f[0];
+                o[1] = f[1];
+                o[2] = f[2] | (((uint32_t)item & 0x3ffu) << 22);
+                o[3] = f[3] | (((uint32_t)item >> 10) << 22);
+                o[4] = f[4];
+            } else {
+                rec_w[6 * ci + 1 + tt] = wd;
+            }
+        }
+        __syncthreads();
+        {
+            const int nl = (int)s_nlong, ns = (int)s_nshort;
+            for (int g = tid; g < nl + ns; g += k7Threads) {
+                const bool is_long = g < nl;
+                const uint32_t slot = is_long ? (uint32_t)g : (uint32_t)(k7FieldItems - 1 - (g - nl));
+                const uint32_t *o = fb + 5 * slot;
+                uint32_t f[5] = {o[0], o[1], o[2], o[3], o[4]};
+                const int item = (int)((f[2] >> 22) | ((f[3] >> 22) << 10));
+                f[2] &= 0x3fffffu;
+                f[3] &= 0x3fffffu;
+                const uint32_t df = df_of_fields(f);
+                uint32_t wd;
+                if (is_long) {
+                    const uint32_t syn = syn112_fields(tabs, f);
+                    if (df == 17 || df == 18)          // mode_s/mod.rs:91-109
+                        wd = syn ? 0u : (((df == 17 ? K_DF17 : K_DF18) << 29) | msg_bits<8, 24>(f));
+                    else                                // :110-134
+                        wd = (K_PAR_LONG << 29) | syn;
+                } else {
+                    const uint32_t syn = syn56_fields(tabs, f);
+                    if (df == 11)                       // :73-90
+                        wd = (syn & 0xffff80u) ? 0u
+                                               : ((((syn & 0x7f) ? K_DF11_IID : K_DF11_IID0) << 29) | msg_bits<8, 24>(f));
+                    else                                // :56-72
+                        wd = (K_PAR_SHORT << 29) | syn;
+                }
+                const int ci = item / 5, tt = item - 5 * ci;
+                rec_w[6 * ci + 1 + tt] = wd;
+                const uint32_t kind = wd >> 29;
+                if (kind == K_DF11_IID0 || kind == K_DF17 || kind == K_DF18) {
+                    const uint32_t key = (wd & 0xffffffu) | (kind == K_DF18 ? B200ADSB_ICAO_FILTER_ADSB_NT : 0u);
+                    const uint32_t j = (uint32_t)(tile_start + cand[ci]);
+                    event_add(p.ev_keys, p.ev_ord, p.ev_used, p.ev_mask, p.counters, key,
+                              ord_buf | ((unsigned long long)j << 3) | (unsigned long long)tt);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            s_nlong = 0;
+            s_nshort = 0;
+        }
+    }
+}
+
+}  // namespace b200
