@@ -36,7 +36,10 @@ constexpr int k7CandCap = 128;              // survivors decoded per window
 constexpr int k7FieldItems = 5 * k7CandCap;
 constexpr int k7ListCap = 1024;             // template matches gated per round
 #ifndef B200_SCAN7_MIN_BLOCKS
-#define B200_SCAN7_MIN_BLOCKS 6
+#define B200_SCAN7_MIN_BLOCKS 7
+#endif
+#ifndef B200_SCAN7_RING
+#define B200_SCAN7_RING 3                   // IQ rows in flight per lane (cp.async ring); 0: register prefetch
 #endif
 
 // shared memory plan for tile size T
@@ -58,8 +61,8 @@ struct Scan7Smem {
         off_surv = o;
         o += (size_t)nw * 4;
         o = (o + 15) & ~(size_t)15;
-        off_masks = o;                                // [5][12][WP] template match masks
-        o += (size_t)5 * 12 * WP * 4;
+        off_masks = o;                                // per-lane ring of IQ rows in flight (cp.async), 16 B each
+        o += (size_t)k7Threads * B200_SCAN7_RING * 16;
         off_list = o;
         o += (size_t)k7ListCap * 2;
         off_cand = o;
@@ -80,7 +83,7 @@ struct Row {
 };
 
 template <bool FROM_MAG>
-__device__ __forceinline__ Row row_slow(const ScanParams &p, const uint32_t *b32, const uint16_t *d16, int s,
+__device__ __noinline__ Row row_slow(const ScanParams &p, const uint32_t *b32, const uint16_t *d16, int s,
                                         int i, int len, const uint32_t *prev, int prev_len)
 {
     Row r;
@@ -174,6 +177,73 @@ __device__ __forceinline__ void gate_eval7(const uint16_t *mag, uint32_t *surv, 
         return;
     gate_eval(mag, surv, mi, cs);
 }
+__device__ __noinline__ void gate_eval7_cold(const uint16_t *mag, uint32_t *surv, int mi, uint32_t cs, int npos)
+{
+    gate_eval7(mag, surv, mi, cs, npos);
+}
+
+// P3a for the residues rho0..rho0+2 (see the kernel).  XR[i] / XF[i] is the rising / falling
+// plane word for edge offset s = i - dr of a position with residue rho0 + dr: row t = rho0 + i
+// mod 12, shifted by one bit when t >= 12.
+__device__ __forceinline__ void p3a_rows(const int rho0, const uint32_t *planes, int WP, int nwq, int lane,
+                                         uint16_t *list, uint32_t *s_total, const uint16_t *mag, uint32_t *surv,
+                                         int npos)
+{
+    const uint32_t *Rp = planes + 5 * 12 * WP, *Fp = planes + 6 * 12 * WP;
+    const int w = lane;
+    const bool act = w < nwq;
+    uint32_t XR[15], XF[15];
+#pragma unroll
+    for (int i = 0; i < 15; i++) {
+        const int t = rho0 + i;
+        const int sh = t >= 12 ? 1 : 0;
+        const int o = (t - 12 * sh) * WP + w;
+        XR[i] = act ? __funnelshift_r(Rp[o], Rp[o + 1], sh) : 0u;
+        XF[i] = act ? __funnelshift_r(Fp[o], Fp[o + 1], sh) : 0u;
+    }
+#pragma unroll
+    for (int dr = 0; dr < 3; dr++) {
+        const int rho = rho0 + dr;
+#define ER(s) XR[dr + (s)]
+#define EF(s) XF[dr + (s)]
+        const uint32_t quick = ER(0) & EF(12);   // p0 < p1 && p12 > p13 (:221)
+        const uint32_t T3 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(10);
+        const uint32_t T4 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(11);
+        const uint32_t T5 = EF(1) & ER(2) & EF(4) & ER(8) & EF(10) & ER(11);
+        const uint32_t T6 = EF(1) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+        const uint32_t T7 = EF(2) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+#undef ER
+#undef EF
+        // first match wins (:226-317); case number as three bit planes
+        uint32_t any = quick & (T3 | T4 | T5 | T6 | T7);
+        const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5), c4 = ~(T3 | T4 | T5 | T6);
+        const uint32_t b0 = c1 | c3, b1 = c2 | c3;
+        const int cnt = __popc(any);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        int base = 0;
+        if (lane == 31 && incl)
+            base = (int)atomicAdd(s_total, (uint32_t)incl);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        int off = base + incl - cnt;
+        while (any) {
+            const int bit = __ffs(any) - 1;
+            any &= any - 1;
+            const uint32_t cs = ((b0 >> bit) & 1u) | (((b1 >> bit) & 1u) << 1) | (((c4 >> bit) & 1u) << 2);
+            const int mi = 12 * (32 * w + bit) + rho;
+            if (off < k7ListCap)
+                list[off] = (uint16_t)(mi | (cs << 13));
+            else
+                gate_eval7_cold(mag, surv, mi, cs, npos);   // list full: evaluate in place (out of line)
+            off++;
+        }
+    }
+}
 
 template <bool FROM_MAG>
 __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel(const Scan7Params P)
@@ -184,7 +254,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     uint32_t *fb = reinterpret_cast<uint32_t *>(smem);                      // P4: staged fields (mag is dead)
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + P.off_planes);   // [7][12][WP]
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + P.off_surv);
-    uint32_t *masks = reinterpret_cast<uint32_t *>(smem + P.off_masks);     // [5][12][WP]
+    unsigned char *ring = smem + P.off_masks;                                // [B200_SCAN7_RING][k7Threads] x 16 B
     uint16_t *list = reinterpret_cast<uint16_t *>(smem + P.off_list);
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + P.off_cand);
     const uint32_t *tabs = p.crc_tabs;
@@ -244,7 +314,14 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             const bool fast = !FROM_MAG && p.vec_ok && s0 + g_lo >= 0 && s0 + g_hi <= len;
             {
                 const int rb = k7Group * (G + 1);                  // first row of the next group
-                const Row rbnd = row_slow<FROM_MAG>(p, b32, d16, s0 + rb, i0 + rb, len, prev, prev_len);
+                Row rbnd;
+                if (fast) {
+                    const int4 v = __ldg(reinterpret_cast<const int4 *>(b32 + s0 + rb));
+                    rbnd.q0 = mag_pair_fast2((uint32_t)v.x, (uint32_t)v.z);
+                    rbnd.q1 = mag_pair_fast2((uint32_t)v.y, (uint32_t)v.w);
+                } else {
+                    rbnd = row_slow<FROM_MAG>(p, b32, d16, s0 + rb, i0 + rb, len, prev, prev_len);
+                }
                 float x, y;
                 f2_unpack(rbnd.q0, st.pm0, st.pm2);
                 f2_unpack(rbnd.q1, st.pm1, y);
@@ -252,7 +329,40 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             }
             uint16_t *mrow = mag + r0 + 12 * (k7Slots - 1);
             if (fast) {
-                // running pointers, two slots per iteration (no register rotation), one pair of prefetch
+#if B200_SCAN7_RING > 0
+                // rows travel global -> shared with cp.async (no registers held while in flight): the lane's
+                // private ring keeps B200_SCAN7_RING rows ahead of the one being processed
+                const char *gsrc = reinterpret_cast<const char *>(b32 + s0 + r0) + 48 * (k7Slots - 1);
+                const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring) + 16u * (uint32_t)tid;
+                constexpr uint32_t kRingStride = 16u * k7Threads;
+#pragma unroll
+                for (int d = 0; d < B200_SCAN7_RING; d++) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + d * kRingStride),
+                                 "l"(gsrc - 48 * d));
+                    asm volatile("cp.async.commit_group;");
+                }
+                gsrc -= 48 * B200_SCAN7_RING;
+                uint32_t rp = ring0;
+#pragma unroll 2
+                for (int k = k7Slots - 1; k >= 0; k--) {
+                    asm volatile("cp.async.wait_group %0;" ::"n"(B200_SCAN7_RING - 1));
+                    uint32_t x, y, z, ww;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(ww) : "r"(rp));
+                    if (k >= B200_SCAN7_RING)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rp), "l"(gsrc));
+                    asm volatile("cp.async.commit_group;");
+                    gsrc -= 48;
+                    rp += kRingStride;
+                    if (rp == ring0 + B200_SCAN7_RING * kRingStride)
+                        rp = ring0;
+                    Row r;
+                    r.q0 = mag_pair_fast2(x, z);
+                    r.q1 = mag_pair_fast2(y, ww);
+                    dense_slot(st, r, is_c0, src_lane, mrow, own);
+                    mrow -= 12;
+                }
+#else
+                // running pointers, two slots per iteration (no register rotation), one row of prefetch
                 const int4 *src = reinterpret_cast<const int4 *>(b32 + s0 + r0) + 3 * (k7Slots - 1);
                 int4 va = __ldg(src), vb;
 #pragma unroll 1
@@ -270,6 +380,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                     dense_slot(st, r, is_c0, src_lane, mrow - 12, own);
                     mrow -= 24;
                 }
+#endif
             } else {
 #pragma unroll 1
                 for (int k = k7Slots - 1; k >= 0; k--) {
@@ -291,114 +402,20 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     }
     __syncthreads();
 
-    // ---- P3a: preamble templates (demod_2400.rs:221-317).  Warp 0, lane = word column w: the 32
-    // positions 12*(32w+bit)+rho for every residue rho (static).  Edge bit at offset s of such a
-    // position is bit (bit + carry) of row (rho+s) mod 12, carry = (rho+s) / 12.
-    if (warp == 0) {
-        const uint32_t *Rp = planes + 5 * 12 * WP, *Fp = planes + 6 * 12 * WP;
-        for (int w = lane; w < nwq; w += 32) {
-            // sliding windows over t = rho + s: XR[t], XF[t] for t in [rho, rho+12]
-            uint32_t XR[24], XF[24];
-#pragma unroll
-            for (int t = 0; t < 24; t++) {
-                if (t < 12) {
-                    XR[t] = Rp[t * WP + w];
-                    XF[t] = Fp[t * WP + w];
-                } else {
-                    XR[t] = __funnelshift_r(Rp[(t - 12) * WP + w], Rp[(t - 12) * WP + w + 1], 1);
-                    XF[t] = __funnelshift_r(Fp[(t - 12) * WP + w], Fp[(t - 12) * WP + w + 1], 1);
-                }
-            }
-#pragma unroll
-            for (int rho = 0; rho < 12; rho++) {
-#define ER(s) XR[rho + (s)]
-#define EF(s) XF[rho + (s)]
-                const uint32_t quick = ER(0) & EF(12);   // p0 < p1 && p12 > p13 (:221)
-                const uint32_t T3 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(10);
-                const uint32_t T4 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(11);
-                const uint32_t T5 = EF(1) & ER(2) & EF(4) & ER(8) & EF(10) & ER(11);
-                const uint32_t T6 = EF(1) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
-                const uint32_t T7 = EF(2) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
-#undef ER
-#undef EF
-                // first match wins (:226-317)
-                const uint32_t M0 = quick & T3;
-                const uint32_t M1 = quick & T4 & ~T3;
-                const uint32_t M2 = quick & T5 & ~(T3 | T4);
-                const uint32_t M3 = quick & T6 & ~(T3 | T4 | T5);
-                const uint32_t M4 = quick & T7 & ~(T3 | T4 | T5 | T6);
-                masks[(0 * 12 + rho) * WP + w] = M0;
-                masks[(1 * 12 + rho) * WP + w] = M1;
-                masks[(2 * 12 + rho) * WP + w] = M2;
-                masks[(3 * 12 + rho) * WP + w] = M3;
-                masks[(4 * 12 + rho) * WP + w] = M4;
-            }
-        }
-    }
+    // ---- P3a: preamble templates (demod_2400.rs:221-317).  Warp wq takes the residues 3wq..3wq+2
+    // (static), lane = word column w: the 32 positions 12*(32w+bit)+rho.  Matches are appended to
+    // one list (order is irrelevant: the gates only set survivor bits).
+    if (tid == 0)
+        s_count = 0;
     __syncthreads();
-
-    // ---- P3b: ordered compaction of the match masks (case-major) and the gates
+    p3a_rows(3 * warp, planes, WP, nwq, lane, list, &s_count, mag, surv, npos);
+    __syncthreads();
+    // ---- P3b: SNR and quiet-zone gates, one match per thread
     {
-        const int nrows = 5 * 12;
-        const int nwords = nrows * nwq;                    // word i <-> (row = i / nwq, w = i % nwq)
-        const int chunk = (nwords + k7Threads - 1) / k7Threads;
-        const int i_lo = min(tid * chunk, nwords), i_hi = min(i_lo + chunk, nwords);
-        int row = i_lo / nwq, w = i_lo - row * nwq;
-        const int row0 = row, w0 = w;
-        int cnt = 0;
-        for (int i = i_lo; i < i_hi; i++) {
-            cnt += __popc(masks[row * WP + w]);
-            if (++w == nwq) {
-                w = 0;
-                row++;
-            }
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        if (lane == 31)
-            s_warp_tot[warp] = (uint32_t)incl;
-        __syncthreads();
-        int my_off = incl - cnt, total = 0;
-#pragma unroll
-        for (int wi = 0; wi < k7Warps; wi++) {
-            const int t = (int)s_warp_tot[wi];
-            if (wi < warp)
-                my_off += t;
-            total += t;
-        }
-        for (int base = 0; base < total; base += k7ListCap) {
-            if (cnt && my_off < base + k7ListCap && my_off + cnt > base) {
-                int off = my_off;
-                row = row0;
-                w = w0;
-                for (int i = i_lo; i < i_hi; i++) {
-                    uint32_t m = masks[row * WP + w];
-                    const int cs = row / 12, rho = row - 12 * cs;
-                    while (m) {
-                        const int bit = __ffs(m) - 1;
-                        m &= m - 1;
-                        if (off >= base && off < base + k7ListCap)
-                            list[off - base] = (uint16_t)((12 * (32 * w + bit) + rho) | (cs << 13));
-                        off++;
-                    }
-                    if (++w == nwq) {
-                        w = 0;
-                        row++;
-                    }
-                }
-            }
-            __syncthreads();
-            const int n = min(k7ListCap, total - base);
-            for (int g = tid; g < n; g += k7Threads) {
-                const uint32_t e = list[g];
-                gate_eval7(mag, surv, (int)(e & 0x1fffu), e >> 13, npos);
-            }
-            __syncthreads();
+        const int n = min((int)s_count, k7ListCap);
+        for (int g = tid; g < n; g += k7Threads) {
+            const uint32_t e = list[g];
+            gate_eval7(mag, surv, (int)(e & 0x1fffu), e >> 13, npos);
         }
     }
     __syncthreads();
