@@ -61,8 +61,11 @@ struct Scan7Smem {
         off_surv = o;
         o += (size_t)nw * 4;
         o = (o + 15) & ~(size_t)15;
-        off_masks = o;                                // per-lane ring of IQ rows in flight (cp.async), 16 B each
-        o += (size_t)k7Threads * B200_SCAN7_RING * 16;
+        off_masks = o;                                // per-lane ring of IQ rows in flight (cp.async), 16 B each;
+        {                                             // later the template match masks [12][WP] x 16 B
+            const size_t ring_b = (size_t)k7Threads * B200_SCAN7_RING * 16, mask_b = (size_t)12 * WP * 16;
+            o += ring_b > mask_b ? ring_b : mask_b;
+        }
         off_list = o;
         o += (size_t)k7ListCap * 2;
         off_cand = o;
@@ -182,67 +185,33 @@ __device__ __noinline__ void gate_eval7_cold(const uint16_t *mag, uint32_t *surv
     gate_eval7(mag, surv, mi, cs, npos);
 }
 
-// P3a for the residues rho0..rho0+2 (see the kernel).  XR[i] / XF[i] is the rising / falling
-// plane word for edge offset s = i - dr of a position with residue rho0 + dr: row t = rho0 + i
-// mod 12, shifted by one bit when t >= 12.
-__device__ __forceinline__ void p3a_rows(const int rho0, const uint32_t *planes, int WP, int nwq, int lane,
-                                         uint16_t *list, uint32_t *s_total, const uint16_t *mag, uint32_t *surv,
-                                         int npos)
+// SNR and quiet-zone gates of one template match (demod_2400.rs:129,135-146) without a branch
+// per template case.  With a=p1 h=p2 b=p3 e=p4 c=p9 f=p10 g=p11 d=p12 (demod_2400.rs:226-317):
+//   case   high*4            signal        noise
+//   0 (3)  a+b+c+g+d         a+b+c         p5+p6+p7
+//   1 (4)  a+b+c+d           a+b+c+d       p5+p6+p7+p8
+//   2 (5)  a+b+e+c+f+d       a+d           p6+p7
+//   3 (6)  a+e+f+d           a+e+f+d       p5+p6+p7+p8
+//   4 (7)  a+h+e+f+d         e+f+d         p6+p7+p8
+__device__ __forceinline__ void gate_eval_bf(const uint16_t *mag, uint32_t *surv, int mi, uint32_t cs, int npos)
 {
-    const uint32_t *Rp = planes + 5 * 12 * WP, *Fp = planes + 6 * 12 * WP;
-    const int w = lane;
-    const bool act = w < nwq;
-    uint32_t XR[15], XF[15];
-#pragma unroll
-    for (int i = 0; i < 15; i++) {
-        const int t = rho0 + i;
-        const int sh = t >= 12 ? 1 : 0;
-        const int o = (t - 12 * sh) * WP + w;
-        XR[i] = act ? __funnelshift_r(Rp[o], Rp[o + 1], sh) : 0u;
-        XF[i] = act ? __funnelshift_r(Fp[o], Fp[o + 1], sh) : 0u;
-    }
-#pragma unroll
-    for (int dr = 0; dr < 3; dr++) {
-        const int rho = rho0 + dr;
-#define ER(s) XR[dr + (s)]
-#define EF(s) XF[dr + (s)]
-        const uint32_t quick = ER(0) & EF(12);   // p0 < p1 && p12 > p13 (:221)
-        const uint32_t T3 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(10);
-        const uint32_t T4 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(11);
-        const uint32_t T5 = EF(1) & ER(2) & EF(4) & ER(8) & EF(10) & ER(11);
-        const uint32_t T6 = EF(1) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
-        const uint32_t T7 = EF(2) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
-#undef ER
-#undef EF
-        // first match wins (:226-317); case number as three bit planes
-        uint32_t any = quick & (T3 | T4 | T5 | T6 | T7);
-        const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5), c4 = ~(T3 | T4 | T5 | T6);
-        const uint32_t b0 = c1 | c3, b1 = c2 | c3;
-        const int cnt = __popc(any);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        int base = 0;
-        if (lane == 31 && incl)
-            base = (int)atomicAdd(s_total, (uint32_t)incl);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        int off = base + incl - cnt;
-        while (any) {
-            const int bit = __ffs(any) - 1;
-            any &= any - 1;
-            const uint32_t cs = ((b0 >> bit) & 1u) | (((b1 >> bit) & 1u) << 1) | (((c4 >> bit) & 1u) << 2);
-            const int mi = 12 * (32 * w + bit) + rho;
-            if (off < k7ListCap)
-                list[off] = (uint16_t)(mi | (cs << 13));
-            else
-                gate_eval7_cold(mag, surv, mi, cs, npos);   // list full: evaluate in place (out of line)
-            off++;
-        }
-    }
+    const int jl = mi - kHaloFront;
+    if (jl < 0 || jl >= npos)
+        return;
+    const uint16_t *pp = mag + mi;
+    const int a = pp[1], h = pp[2], b = pp[3], e = pp[4], n5 = pp[5], n6 = pp[6], n7 = pp[7], n8 = pp[8];
+    const int c = pp[9], f = pp[10], g = pp[11], d = pp[12];
+    const int bc = b + c, ef = e + f;
+    const int H = a + d + (cs < 3 ? bc : 0) + (cs >= 2 ? ef : 0) + (cs == 0 ? g : 0) + (cs == 4 ? h : 0);
+    const int S = (cs < 4 ? a : 0) + (cs < 2 ? bc : 0) + (cs >= 1 ? d : 0) + (cs >= 3 ? ef : 0);
+    const int N = n6 + n7 + (((0x0Bu >> cs) & 1u) ? n5 : 0) + (((0x1Au >> cs) & 1u) ? n8 : 0);
+    if (2 * S < 3 * N)            // demod_2400.rs:129
+        return;
+    const int mx = max(max(max(n5, n6), max(n7, n8)),
+                       max(max(max((int)pp[14], (int)pp[15]), max((int)pp[16], (int)pp[17])), (int)pp[18]));
+    if (mx >= (H >> 2))           // demod_2400.rs:135-146 (high = sum / 4, non-negative)
+        return;
+    atomicOr(&surv[jl >> 5], 1u << (jl & 31));
 }
 
 template <bool FROM_MAG>
@@ -255,11 +224,11 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + P.off_planes);   // [7][12][WP]
     uint32_t *surv = reinterpret_cast<uint32_t *>(smem + P.off_surv);
     unsigned char *ring = smem + P.off_masks;                                // [B200_SCAN7_RING][k7Threads] x 16 B
+    uint32_t *masks = reinterpret_cast<uint32_t *>(smem + P.off_masks);     // P3: [12][nwq] x (match, case planes); the ring is dead
     uint16_t *list = reinterpret_cast<uint16_t *>(smem + P.off_list);
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + P.off_cand);
     const uint32_t *tabs = p.crc_tabs;
     const uint32_t *lut = p.lut;
-    __shared__ uint32_t s_warp_tot[k7Warps];
     __shared__ uint32_t s_base, s_count, s_ok, s_nlong, s_nshort;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -402,30 +371,109 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     }
     __syncthreads();
 
-    // ---- P3a: preamble templates (demod_2400.rs:221-317).  Warp wq takes the residues 3wq..3wq+2
-    // (static), lane = word column w: the 32 positions 12*(32w+bit)+rho.  Matches are appended to
-    // one list (order is irrelevant: the gates only set survivor bits).
-    if (tid == 0)
-        s_count = 0;
+    // ---- P3a: preamble templates (demod_2400.rs:221-317).  Warp 0, lane = word column w, residue
+    // static: the 32 positions 12*(32w+bit)+rho.  Edge bit at offset s of such a position is bit
+    // (bit + carry) of row (rho+s) mod 12, carry = (rho+s) / 12.  Output per (rho, w): the match mask
+    // and the template case as three bit planes.
+    if (warp == 0) {
+        const uint32_t *Rp = planes + 5 * 12 * WP, *Fp = planes + 6 * 12 * WP;
+        if (tid == 0)
+            s_count = 0;
+        for (int w = lane; w < nwq; w += 32) {
+            uint32_t XR[24], XF[24];
+#pragma unroll
+            for (int t = 0; t < 24; t++) {
+                if (t < 12) {
+                    XR[t] = Rp[t * WP + w];
+                    XF[t] = Fp[t * WP + w];
+                } else {
+                    XR[t] = __funnelshift_r(Rp[(t - 12) * WP + w], Rp[(t - 12) * WP + w + 1], 1);
+                    XF[t] = __funnelshift_r(Fp[(t - 12) * WP + w], Fp[(t - 12) * WP + w + 1], 1);
+                }
+            }
+            uint4 *mout = reinterpret_cast<uint4 *>(masks) + w;
+#pragma unroll
+            for (int rho = 0; rho < 12; rho++) {
+#define ER(s) XR[rho + (s)]
+#define EF(s) XF[rho + (s)]
+                const uint32_t quick = ER(0) & EF(12);   // p0 < p1 && p12 > p13 (:221)
+                const uint32_t T3 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(10);
+                const uint32_t T4 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(11);
+                const uint32_t T5 = EF(1) & ER(2) & EF(4) & ER(8) & EF(10) & ER(11);
+                const uint32_t T6 = EF(1) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+                const uint32_t T7 = EF(2) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+#undef ER
+#undef EF
+                // first match wins (:226-317)
+                const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5);
+                mout[rho * nwq] = make_uint4(quick & (T3 | T4 | T5 | T6 | T7), c1 | c3, c2 | c3,
+                                             ~(T3 | T4 | T5 | T6));
+            }
+        }
+    }
     __syncthreads();
-    p3a_rows(3 * warp, planes, WP, nwq, lane, list, &s_count, mag, surv, npos);
+    // ---- P3b: expand the match masks into one list (order is irrelevant: the gates only set
+    // survivor bits): a warp takes 32 (rho, w) words per round
+    {
+        const uint4 *min4 = reinterpret_cast<const uint4 *>(masks);
+        const int nwords = 12 * nwq;
+        for (int i0w = 32 * warp; i0w < nwords; i0w += 32 * k7Warps) {
+            const int i = i0w + lane;
+            uint4 m = make_uint4(0u, 0u, 0u, 0u);
+            if (i < nwords)
+                m = min4[i];
+            const int cnt = __popc(m.x);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            int base = 0;
+            if (lane == 31 && incl)
+                base = (int)atomicAdd(&s_count, (uint32_t)incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int off = base + incl - cnt;
+            const int rho = i / nwq, w = i - rho * nwq;
+            const int mi0 = 12 * 32 * w + rho;
+            uint32_t any = m.x;
+            while (any) {
+                const int bit = __ffs(any) - 1;
+                any &= any - 1;
+                const uint32_t cs = ((m.y >> bit) & 1u) | (((m.z >> bit) & 1u) << 1) | (((m.w >> bit) & 1u) << 2);
+                const int mi = mi0 + 12 * bit;
+                if (off < k7ListCap)
+                    list[off] = (uint16_t)(mi | (cs << 13));
+                else
+                    gate_eval7_cold(mag, surv, mi, cs, npos);   // list full: evaluate in place (out of line)
+                off++;
+            }
+        }
+    }
     __syncthreads();
-    // ---- P3b: SNR and quiet-zone gates, one match per thread
+    // ---- P3c: SNR and quiet-zone gates, one match per thread
     {
         const int n = min((int)s_count, k7ListCap);
         for (int g = tid; g < n; g += k7Threads) {
             const uint32_t e = list[g];
-            gate_eval7(mag, surv, (int)(e & 0x1fffu), e >> 13, npos);
+            gate_eval_bf(mag, surv, (int)(e & 0x1fffu), e >> 13, npos);
         }
     }
     __syncthreads();
 
-    // ---- P4a: count survivors, reserve pool space (positions are emitted in ascending j)
-    const int wi0 = 2 * tid;                                // two survivor words per thread (nw <= 256)
-    const uint32_t wv0 = (wi0 < P.nw) ? surv[wi0] : 0u, wv1 = (wi0 + 1 < P.nw) ? surv[wi0 + 1] : 0u;
-    int my_off;
-    {
-        const int cnt = __popc(wv0) + __popc(wv1);
+    // ---- P4a: count survivors, reserve pool space (positions are emitted in ascending j).  Warp 0
+    // alone: lane l owns the survivor words 8l..8l+7 (nw <= 256), one warp scan, no block barrier.
+    uint32_t wv[8];
+    int my_off = 0;
+    if (warp == 0) {
+        int cnt = 0;
+#pragma unroll
+        for (int h = 0; h < 8; h++) {
+            const int wi = 8 * lane + h;
+            wv[h] = (wi < P.nw) ? surv[wi] : 0u;
+            cnt += __popc(wv[h]);
+        }
         int incl = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -433,20 +481,9 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             if (lane >= o)
                 incl += t;
         }
-        __syncthreads();                                     // s_warp_tot reuse
-        if (lane == 31)
-            s_warp_tot[warp] = (uint32_t)incl;
-        __syncthreads();
         my_off = incl - cnt;
-        uint32_t total = 0;
-#pragma unroll
-        for (int wi = 0; wi < k7Warps; wi++) {
-            const uint32_t t = s_warp_tot[wi];
-            if (wi < warp)
-                my_off += (int)t;
-            total += t;
-        }
-        if (tid == 0) {
+        if (lane == 31) {
+            const uint32_t total = (uint32_t)incl;
             uint32_t base = 0, ok = 1;
             if (total) {
                 base = atomicAdd(&p.counters[C_POOL], total);
@@ -472,16 +509,16 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     const int C = (int)s_count;
     const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
     for (int win = 0; win < C; win += k7CandCap) {
-        {
+        if (warp == 0) {
             int off = my_off;
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-                uint32_t wv2 = h ? wv1 : wv0;
+            for (int h = 0; h < 8; h++) {
+                uint32_t wv2 = wv[h];
                 while (wv2) {
                     const int bit = __ffs(wv2) - 1;
                     wv2 &= wv2 - 1;
                     if (off >= win && off < win + k7CandCap)
-                        cand[off - win] = (uint16_t)((wi0 + h) * 32 + bit);
+                        cand[off - win] = (uint16_t)((8 * lane + h) * 32 + bit);
                     off++;
                 }
             }
