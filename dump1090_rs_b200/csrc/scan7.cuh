@@ -157,9 +157,14 @@ __device__ __forceinline__ void dense_slot(DenseState &st, const Row r, bool is_
     const float m5 = __shfl_sync(0xffffffffu, t1, src_lane);
     const float m6 = __shfl_sync(0xffffffffu, t2, src_lane);
     st.pm0 = m0; st.pm1 = m1; st.pm2 = m2;
-    const u64x q2 = f2_pack(m2, m4), q3 = f2_pack(m3, m5), q4 = f2_pack(m4, m6);
-    const u64x p0 = f2_sub(r.q1, r.q0), p1 = f2_sub(q2, r.q1), p2 = f2_sub(q3, q2), p3 = f2_sub(q4, q3);
-    const u64x n0 = f2_sub(r.q0, r.q1), n1 = f2_sub(r.q1, q2);
+    // first differences as pairs (d0,d2) (d1,d3) (d2,d4) (d3,d5); only the first comes out of aligned
+    // register pairs, the others are cheaper as scalar subtractions written straight into their pair
+    // than as packed ones fed by register moves
+    const u64x p0 = f2_sub(r.q1, r.q0), n0 = f2_sub(r.q0, r.q1);
+    const u64x p1 = f2_pack(__fsub_rn(m2, m1), __fsub_rn(m4, m3));
+    const u64x p2 = f2_pack(__fsub_rn(m3, m2), __fsub_rn(m5, m4));
+    const u64x p3 = f2_pack(__fsub_rn(m4, m3), __fsub_rn(m6, m5));
+    const u64x n1 = f2_pack(__fsub_rn(m1, m2), __fsub_rn(m3, m4));
     float a, b;
     f2_unpack(p0, a, b); st.acc[0][6] = sgn_in(a, st.acc[0][6]); st.acc[2][6] = sgn_in(b, st.acc[2][6]);   // falling
     f2_unpack(p1, a, b); st.acc[1][6] = sgn_in(a, st.acc[1][6]); st.acc[3][6] = sgn_in(b, st.acc[3][6]);
