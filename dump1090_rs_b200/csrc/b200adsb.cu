@@ -212,13 +212,16 @@ int pick_tile(const b200adsb_ctx *c, size_t n_buffers, size_t spb)
         return c->tile_opt;
     // tile sizes whose halo-extended length is a whole number of 384-sample blocks;
     // the largest that still gives every SM a few tiles
-    static const int kTiles[] = {kDefaultTile, 3544, 2008, 856, 472};
-    for (int t : kTiles) {
+    static const int kTiles6[] = {kDefaultTile, 3544, 2008, 856, 472};
+    static const int kTiles7[] = {kDefaultTile, 3544, 1624, 1624, 1624};   // v7: whole warps of 10 groups x 192 samples
+    const int *kTiles = c->scan_ver >= 7 ? kTiles7 : kTiles6;
+    for (int ti = 0; ti < 5; ti++) {
+        const int t = kTiles[ti];
         const size_t tiles = n_buffers * ((spb + t - 1) / t);
         if (tiles >= 592)
             return t;
     }
-    return 472;
+    return kTiles[4];
 }
 
 void prof_begin(b200adsb_ctx *c, std::vector<EventPair> &v)
@@ -388,6 +391,8 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
         P7.NG = L7.NG;
         P7.WP = L7.WP;
         P7.nw = L7.nw;
+        P7.Wrow = (L7.NG + 1) / 2;
+        P7.inv_Wrow = (65536 + P7.Wrow - 1) / P7.Wrow;
         size_t bytes7 = L7.bytes;
         if (const char *ex = getenv("B200ADSB_DEBUG_EXTRA_SMEM"))
             bytes7 += (size_t)atoi(ex);

@@ -78,6 +78,7 @@ struct Scan7Params {
     ScanParams s;
     uint32_t off_planes, off_surv, off_masks, off_list, off_cand;
     int NG, WP, nw;
+    int Wrow, inv_Wrow;    // mask words per residue row for this tile size; ceil(65536 / Wrow): i / Wrow == (i * inv) >> 16 for i < 12 * Wrow
 };
 
 // one row of four consecutive magnitudes, as f32 bit patterns 2^23 + m, paired (m0,m2) (m1,m3)
@@ -411,7 +412,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
 #undef EF
                 // first match wins (:226-317)
                 const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5);
-                mout[rho * nwq] = make_uint4(quick & (T3 | T4 | T5 | T6 | T7), c1 | c3, c2 | c3,
+                mout[rho * P.Wrow] = make_uint4(quick & (T3 | T4 | T5 | T6 | T7), c1 | c3, c2 | c3,
                                              ~(T3 | T4 | T5 | T6));
             }
         }
@@ -421,11 +422,12 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     // survivor bits): a warp takes 32 (rho, w) words per round
     {
         const uint4 *min4 = reinterpret_cast<const uint4 *>(masks);
-        const int nwords = 12 * nwq;
+        const int nwords = 12 * P.Wrow;
         for (int i0w = 32 * warp; i0w < nwords; i0w += 32 * k7Warps) {
             const int i = i0w + lane;
+            const int rho = (int)(((uint32_t)i * (uint32_t)P.inv_Wrow) >> 16), w = i - rho * P.Wrow;   // i / Wrow (exact, checked for every Wrow <= 23)
             uint4 m = make_uint4(0u, 0u, 0u, 0u);
-            if (i < nwords)
+            if (i < nwords && w < nwq)
                 m = min4[i];
             const int cnt = __popc(m.x);
             int incl = cnt;
@@ -440,18 +442,17 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 base = (int)atomicAdd(&s_count, (uint32_t)incl);
             base = __shfl_sync(0xffffffffu, base, 31);
             int off = base + incl - cnt;
-            const int rho = i / nwq, w = i - rho * nwq;
             const int mi0 = 12 * 32 * w + rho;
             uint32_t any = m.x;
             while (any) {
                 const int bit = __ffs(any) - 1;
                 any &= any - 1;
-                const uint32_t cs = ((m.y >> bit) & 1u) | (((m.z >> bit) & 1u) << 1) | (((m.w >> bit) & 1u) << 2);
-                const int mi = mi0 + 12 * bit;
-                if (off < k7ListCap)
-                    list[off] = (uint16_t)(mi | (cs << 13));
-                else
-                    gate_eval7_cold(mag, surv, mi, cs, npos);   // list full: evaluate in place (out of line)
+                if (off < k7ListCap) {
+                    list[off] = (uint16_t)(i | (bit << 10));       // (mask word, bit); the gate thread decodes
+                } else {                                            // list full: evaluate in place (out of line)
+                    const uint32_t cs = ((m.y >> bit) & 1u) | (((m.z >> bit) & 1u) << 1) | (((m.w >> bit) & 1u) << 2);
+                    gate_eval7_cold(mag, surv, mi0 + 12 * bit, cs, npos);
+                }
                 off++;
             }
         }
@@ -459,10 +460,15 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     __syncthreads();
     // ---- P3c: SNR and quiet-zone gates, one match per thread
     {
+        const uint4 *min4 = reinterpret_cast<const uint4 *>(masks);
         const int n = min((int)s_count, k7ListCap);
         for (int g = tid; g < n; g += k7Threads) {
             const uint32_t e = list[g];
-            gate_eval_bf(mag, surv, (int)(e & 0x1fffu), e >> 13, npos);
+            const int i = (int)(e & 0x3ffu), bit = (int)(e >> 10);
+            const uint4 m = min4[i];
+            const uint32_t cs = ((m.y >> bit) & 1u) | (((m.z >> bit) & 1u) << 1) | (((m.w >> bit) & 1u) << 2);
+            const int rho = (int)(((uint32_t)i * (uint32_t)P.inv_Wrow) >> 16), w = i - rho * P.Wrow;
+            gate_eval_bf(mag, surv, 12 * (32 * w + bit) + rho, cs, npos);
         }
     }
     __syncthreads();
