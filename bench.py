@@ -255,6 +255,8 @@ def main() -> int:
     value = total_samples * args.steps / (ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (scan): algorithmic bytes = 4 B per IQ sample
+    SCAN_KERNEL = {"6": "scan_kernel<false>", "8": "dense8_kernel<false> + sparse8_kernel"}.get(
+        os.environ.get("B200ADSB_SCAN", "7"), "scan7_kernel<false>")
     peak, peak_src = peaks()
     # (the scan kernel is launched once per chunk of tiles; sum over the timed region)
     scan_launches = max(tim["scan_launches"], 1)
@@ -272,7 +274,7 @@ def main() -> int:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
-                "kernel": "scan_kernel<false>", "kernel_ms_per_launch": scan_ms,
+                "kernel": SCAN_KERNEL, "kernel_ms_per_launch": scan_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": (tim["scan_ms"] / ms) if ms else None,
                 "kernel_ms_per_step": tim["scan_ms"] / args.steps,

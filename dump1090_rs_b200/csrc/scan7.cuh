@@ -220,6 +220,50 @@ __device__ __forceinline__ void gate_eval_bf(const uint16_t *mag, uint32_t *surv
     atomicOr(&surv[jl >> 5], 1u << (jl & 31));
 }
 
+#ifndef B200_SCAN7_P3A_SPLIT
+#define B200_SCAN7_P3A_SPLIT 1              // warps sharing the template pass (1, 2 or 4): static residue ranges
+#endif
+// P3a for the residues RHO0..RHO0+NRHO-1, lane = word column w: the 32 positions 12*(32w+bit)+rho.
+// X[i] is the plane word for edge offset s = i - (rho - RHO0): row t = RHO0 + i mod 12, shifted by
+// one bit when t >= 12 (the carry into the next 12-sample period).  Output per (rho, w): the match
+// mask and the template case as three bit planes.
+template <int RHO0, int NRHO>
+__device__ __forceinline__ void p3a_rows(const uint32_t *planes, int WP, int nwq, int lane, uint32_t *masks, int Wrow)
+{
+    const uint32_t *Rp = planes + 5 * 12 * WP, *Fp = planes + 6 * 12 * WP;
+    for (int w = lane; w < nwq; w += 32) {
+        uint32_t XR[NRHO + 12], XF[NRHO + 12];
+#pragma unroll
+        for (int i = 0; i < NRHO + 12; i++) {
+            const int t = RHO0 + i;
+            if (t < 12) {
+                XR[i] = Rp[t * WP + w];
+                XF[i] = Fp[t * WP + w];
+            } else {
+                XR[i] = __funnelshift_r(Rp[(t - 12) * WP + w], Rp[(t - 12) * WP + w + 1], 1);
+                XF[i] = __funnelshift_r(Fp[(t - 12) * WP + w], Fp[(t - 12) * WP + w + 1], 1);
+            }
+        }
+        uint4 *mout = reinterpret_cast<uint4 *>(masks) + w;
+#pragma unroll
+        for (int dr = 0; dr < NRHO; dr++) {
+#define ER(s) XR[dr + (s)]
+#define EF(s) XF[dr + (s)]
+            const uint32_t quick = ER(0) & EF(12);   // p0 < p1 && p12 > p13 (:221)
+            const uint32_t T3 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(10);
+            const uint32_t T4 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(11);
+            const uint32_t T5 = EF(1) & ER(2) & EF(4) & ER(8) & EF(10) & ER(11);
+            const uint32_t T6 = EF(1) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+            const uint32_t T7 = EF(2) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
+#undef ER
+#undef EF
+            // first match wins (:226-317)
+            const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5);
+            mout[(RHO0 + dr) * Wrow] = make_uint4(quick & (T3 | T4 | T5 | T6 | T7), c1 | c3, c2 | c3, ~(T3 | T4 | T5 | T6));
+        }
+    }
+}
+
 template <bool FROM_MAG>
 __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel(const Scan7Params P)
 {
@@ -381,42 +425,24 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     // static: the 32 positions 12*(32w+bit)+rho.  Edge bit at offset s of such a position is bit
     // (bit + carry) of row (rho+s) mod 12, carry = (rho+s) / 12.  Output per (rho, w): the match mask
     // and the template case as three bit planes.
-    if (warp == 0) {
-        const uint32_t *Rp = planes + 5 * 12 * WP, *Fp = planes + 6 * 12 * WP;
-        if (tid == 0)
-            s_count = 0;
-        for (int w = lane; w < nwq; w += 32) {
-            uint32_t XR[24], XF[24];
-#pragma unroll
-            for (int t = 0; t < 24; t++) {
-                if (t < 12) {
-                    XR[t] = Rp[t * WP + w];
-                    XF[t] = Fp[t * WP + w];
-                } else {
-                    XR[t] = __funnelshift_r(Rp[(t - 12) * WP + w], Rp[(t - 12) * WP + w + 1], 1);
-                    XF[t] = __funnelshift_r(Fp[(t - 12) * WP + w], Fp[(t - 12) * WP + w + 1], 1);
-                }
-            }
-            uint4 *mout = reinterpret_cast<uint4 *>(masks) + w;
-#pragma unroll
-            for (int rho = 0; rho < 12; rho++) {
-#define ER(s) XR[rho + (s)]
-#define EF(s) XF[rho + (s)]
-                const uint32_t quick = ER(0) & EF(12);   // p0 < p1 && p12 > p13 (:221)
-                const uint32_t T3 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(10);
-                const uint32_t T4 = EF(1) & ER(2) & EF(3) & ER(8) & EF(9) & ER(11);
-                const uint32_t T5 = EF(1) & ER(2) & EF(4) & ER(8) & EF(10) & ER(11);
-                const uint32_t T6 = EF(1) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
-                const uint32_t T7 = EF(2) & ER(3) & EF(4) & ER(9) & EF(10) & ER(11);
-#undef ER
-#undef EF
-                // first match wins (:226-317)
-                const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5);
-                mout[rho * P.Wrow] = make_uint4(quick & (T3 | T4 | T5 | T6 | T7), c1 | c3, c2 | c3,
-                                             ~(T3 | T4 | T5 | T6));
-            }
-        }
+    if (tid == 0)
+        s_count = 0;
+#if B200_SCAN7_P3A_SPLIT == 1
+    if (warp == 0)
+        p3a_rows<0, 12>(planes, WP, nwq, lane, masks, P.Wrow);
+#elif B200_SCAN7_P3A_SPLIT == 2
+    if (warp == 0)
+        p3a_rows<0, 6>(planes, WP, nwq, lane, masks, P.Wrow);
+    else if (warp == 1)
+        p3a_rows<6, 6>(planes, WP, nwq, lane, masks, P.Wrow);
+#else
+    switch (warp) {
+    case 0: p3a_rows<0, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
+    case 1: p3a_rows<3, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
+    case 2: p3a_rows<6, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
+    default: p3a_rows<9, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
     }
+#endif
     __syncthreads();
     // ---- P3b: expand the match masks into one list (order is irrelevant: the gates only set
     // survivor bits): a warp takes 32 (rho, w) words per round

@@ -33,15 +33,15 @@ for ln, src, v, s in sorted(per, key=lambda p: -p[2])[:top]:
 # ---- per-phase aggregation: phases are delimited by "// ---- Pn" comments in the kernel source
 import re
 src_file = None
-for cand in ("dump1090_rs_b200/csrc/kernels.cuh",):
+for cand in ("dump1090_rs_b200/csrc/scan7.cuh",):
     try:
         src_file = open(cand).read().splitlines()
     except OSError:
         pass
 if src_file:
     marks = [(i + 1, m.group(1)) for i, l in enumerate(src_file) for m in [re.search(r"// ---- (P\w+)", l)] if m]
-    k0 = [i + 1 for i, l in enumerate(src_file) if "scan_kernel(const ScanParams p)" in l]
-    k1 = [i + 1 for i, l in enumerate(src_file) if "to_mag kernel" in l]
+    k0 = [i + 1 for i, l in enumerate(src_file) if "scan7_kernel(const Scan7Params P)" in l]
+    k1 = [len(src_file) + 1]
     agg = {}
     for ln, src, v, s in per:
         if k0 and k1 and k0[0] <= ln < k1[0]:

@@ -17,7 +17,7 @@ print("value %.0f Msps  step %.3f ms  scan %.3f ms decode %.3f ms resolve %.3f m
 PY
 tail -3 gpurun_out/bench_$TAG.err
 if [ "${3:-ncu}" = "ncu" ]; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:^scan_kernel -s 3 -c 1 \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan7_kernel -s 3 -c 1 \
     -o gpurun_out/prof_scan_$TAG python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_$TAG.log 2>&1
   tail -2 gpurun_out/ncu_$TAG.log | cut -c1-200
 fi
