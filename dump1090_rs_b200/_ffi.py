@@ -95,6 +95,8 @@ _PROTOS = {
     "b200adsb_demod_iq_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                           C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                           C.c_void_p]),
+    "b200adsb_demod_iq_batch_dev_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                    C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200adsb_demod_iq_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                               C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                               C.c_void_p]),

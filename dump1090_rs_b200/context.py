@@ -130,6 +130,14 @@ class Context:
                        C.byref(n), counts_ptr or None), "demod_iq_batch(_dev)")
         return int(n.value)
 
+    def demod_iq_batch_async_ptr(self, iq_ptr: int, n_buffers: int, spb: int, stride: int, out_ptr: int,
+                                 cap: int, result_ptr: int, lengths_ptr: int = 0) -> None:
+        """Enqueue-only batch (b200adsb_demod_iq_batch_dev_async): result_ptr -> 4 x uint32 on the
+        device {frames, overflow flags, candidates, frames > cap}; read it after a stream sync."""
+        self._check(self._L.b200adsb_demod_iq_batch_dev_async(self._h, iq_ptr, n_buffers, spb, stride,
+                                                              lengths_ptr or None, out_ptr, cap, result_ptr),
+                    "demod_iq_batch_dev_async")
+
     def scan_batch_dev(self, iq_ptr: int, n_buffers: int, spb: int, stride: int, first_ordinal: int,
                        ordinal_stride: int, lengths_ptr: int = 0):
         self._check(self._L.b200adsb_scan_batch_dev(self._h, iq_ptr, n_buffers, spb, stride,

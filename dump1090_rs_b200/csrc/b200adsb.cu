@@ -510,7 +510,7 @@ int scan_run_all(b200adsb_ctx *c)
 
 // stage 2: finalise events, resolve, ordered emit, commit
 int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
-                uint32_t *d_per_buffer_counts)
+                uint32_t *d_per_buffer_counts, uint32_t *d_async_result = nullptr)
 {
     Pending &q = c->cur;
     if (!q.active)
@@ -601,6 +601,17 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
                                                         c->d_new_keys, c->d_counters, c->d_members);
         CK(c, cudaGetLastError());
         c->timing.other_launches += 5;
+    }
+    if (d_async_result) {
+        // enqueue-only form: the batch outcome stays on the device, nothing is read back here
+        batch_result_kernel<<<1, 32, 0, c->stream>>>(c->d_counters, d_async_result, ep.cap);
+        CK(c, cudaGetLastError());
+        c->timing.other_launches++;
+        prof_end(c, c->other_events);
+        q.active = false;
+        if (save_tail)
+            c->tail_cur ^= 1;
+        return B200ADSB_OK;
     }
     prof_end(c, c->other_events);
     int rc = read_counters(c);
@@ -985,6 +996,26 @@ int b200adsb_resolve_batch_dev(b200adsb_ctx *c, b200adsb_frame *d_out, size_t ca
         return B200ADSB_ERR_EVENTS;
     }
     return rc;
+}
+
+int b200adsb_demod_iq_batch_dev_async(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffers, size_t spb,
+                                      size_t stride, const uint32_t *d_lengths, b200adsb_frame *d_out,
+                                      size_t cap, uint32_t *d_result)
+{
+    if (!c || !d_result)
+        return B200ADSB_ERR_BAD_ARG;
+    if ((!d_iq && n_buffers && spb) || (stride < spb && n_buffers > 1))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = scan_begin(c, d_iq, false, n_buffers, spb, stride, d_lengths, c->next_ordinal, 1);
+    if (rc) return rc;
+    c->next_ordinal += n_buffers;
+    rc = reset_scan_counters(c);
+    if (rc) { c->cur.active = false; return rc; }
+    rc = launch_scan(c, 0, c->cur.n_buffers);
+    if (rc) { c->cur.active = false; return rc; }
+    return resolve_run(c, d_out, cap, nullptr, nullptr, d_result);
 }
 
 int b200adsb_demod_iq_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffers, size_t spb,

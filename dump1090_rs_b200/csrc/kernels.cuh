@@ -1598,6 +1598,17 @@ __global__ void save_tail_kernel(const uint32_t *in, unsigned long long stride, 
 }
 
 // ================================================================== filter helpers
+// outcome of an enqueue-only batch: {frames, flags, candidates, frames > cap}
+__global__ void batch_result_kernel(const uint32_t *counters, uint32_t *out, uint32_t cap)
+{
+    if (threadIdx.x == 0) {
+        out[0] = counters[C_FRAMES];
+        out[1] = counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF);
+        out[2] = counters[C_CAND];
+        out[3] = counters[C_FRAMES] > cap ? 1u : 0u;
+    }
+}
+
 __global__ void filter_add_kernel(uint32_t *members, uint32_t *counters, uint32_t key)
 {
     if (threadIdx.x || blockIdx.x)

@@ -146,6 +146,21 @@ int b200adsb_demod_iq_batch_dev(b200adsb_ctx *ctx, const int16_t *d_iq, size_t n
                                 const uint32_t *d_lengths, b200adsb_frame *d_out, size_t cap,
                                 size_t *n_out, uint32_t *d_per_buffer_counts);
 
+/* Enqueue-only form of b200adsb_demod_iq_batch_dev for device-resident pipelines (the
+ * reference's loop `stream.read -> to_mag -> demodulate2400`, main.rs:161-167, with the
+ * consumer of the frames on the device or reading them later): the call returns as soon as
+ * the batch is queued on the context's stream; nothing is read back.  d_result (device,
+ * 4 x uint32): [0] frames written to d_out in (buffer, j) order, [1] 0, or non-zero when
+ * the optimistic candidate pool / event table overflowed -- that batch was NOT committed to
+ * the filter and wrote no valid frames: rerun it (and the batches queued after it) with the
+ * synchronous call, which grows the pool; [2] positions that passed the preamble gates;
+ * [3] 1 when more than `cap` frames were found.  Batches on one context execute in call
+ * order with one filter, exactly like the synchronous form. */
+int b200adsb_demod_iq_batch_dev_async(b200adsb_ctx *ctx, const int16_t *d_iq, size_t n_buffers,
+                                      size_t samples_per_buffer, size_t stride_samples,
+                                      const uint32_t *d_lengths, b200adsb_frame *d_out, size_t cap,
+                                      uint32_t *d_result);
+
 /* ---- split form for a stream sharded over several GPUs (one context per rank).
  * scan:    stage 1 on this rank's buffers; local buffer b has stream ordinal
  *          first_ordinal + b*ordinal_stride (round robin: first=rank, stride=world).

@@ -477,3 +477,48 @@ def test_carry_option_stream_continuity(pkg, oracle_mod):
     c.icao_flush()
     assert len(c.demod_iq_batch(batch, 4, 25000)) < len(ref)
     c.close()
+
+
+@pytest.mark.gpu
+def test_enqueue_only_batches_match_synchronous_calls(pkg):
+    """b200adsb_demod_iq_batch_dev_async: several batches queued back to back on one context give
+    the frames, counts and filter state of the same batches through the synchronous call."""
+    import torch
+    from dump1090_rs_b200 import synth
+    nbuf, spb, nbatch, cap = 24, 131072, 4, 4096
+    iq = synth.make_batch(77, nbuf * nbatch, msgs_per_buffer=6).reshape(nbatch, nbuf, spb, 2)
+    dev = torch.device("cuda", 0)
+    d_iq = torch.from_numpy(np.ascontiguousarray(iq)).to(dev)
+    stream = torch.cuda.current_stream()
+
+    def run(queued):
+        ctx = pkg.Context(0, stream.cuda_stream)
+        ctx.icao_flush()
+        frames = torch.zeros((nbatch, cap, 28), dtype=torch.uint8, device=dev)
+        res = torch.zeros((nbatch, 4), dtype=torch.int32, device=dev)
+        counts = []
+        if not queued:
+            for k in range(nbatch):
+                counts.append(ctx.demod_iq_batch_ptr(d_iq[k].data_ptr(), nbuf, spb, spb, frames[k].data_ptr(), cap))
+        else:
+            # size the candidate pool once, as a caller's warm-up would; then queue everything
+            ctx.demod_iq_batch_ptr(d_iq[0].data_ptr(), nbuf, spb, spb, frames[0].data_ptr(), cap)
+            ctx.icao_flush()
+            for k in range(nbatch):
+                ctx.demod_iq_batch_async_ptr(d_iq[k].data_ptr(), nbuf, spb, spb, frames[k].data_ptr(), cap,
+                                             res[k].data_ptr())
+            ctx.sync()
+            r = res.cpu().numpy()
+            assert (r[:, 1] == 0).all() and (r[:, 3] == 0).all(), r
+            counts = [int(x) for x in r[:, 0]]
+        snap = sorted(ctx.icao_snapshot())
+        out = [frames[k, :counts[k]].cpu().numpy().tobytes() for k in range(nbatch)]
+        ctx.close()
+        return counts, out, snap
+
+    c_sync, f_sync, s_sync = run(False)
+    c_q, f_q, s_q = run(True)
+    assert sum(c_sync) > 0
+    assert c_q == c_sync
+    assert f_q == f_sync
+    assert s_q == s_sync
