@@ -585,10 +585,12 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
             c->timing.other_launches++;
         }
         if (q.n_tiles) {
+            // one warp per frame; the frame count is only known on the device, so a fixed grid strides
+            const uint32_t eg = (uint32_t)std::min<size_t>(148 * 8, std::max<size_t>(1, (cap + kEmitWarps - 1) / kEmitWarps));
             if (q.from_mag)
-                emit_kernel<true><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
+                emit_frames_kernel<true><<<eg, 32 * kEmitWarps, 0, c->stream>>>(ep, c->d_counters, n_ctas);
             else
-                emit_kernel<false><<<n_ctas, kResolveThreads, 0, c->stream>>>(ep);
+                emit_frames_kernel<false><<<eg, 32 * kEmitWarps, 0, c->stream>>>(ep, c->d_counters, n_ctas);
             CK(c, cudaGetLastError());
         }
         if (save_tail) {

@@ -1550,6 +1550,115 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
     emit_body<FROM_MAG>(p, blockIdx.x);
 }
 
+// Large batches: one warp per FRAME (grid-stride over the batch's frames), so that tiles holding many
+// frames (dense traffic) do not serialise in one warp.  Frame f belongs to the tile found by a
+// binary search over the per-block prefix (32 tiles per resolve block) and a warp scan of that
+// block's 32 tile counts; output slot = f, i.e. (buffer, j) order as before.
+constexpr int kEmitWarps = 8;
+template <bool FROM_MAG>
+__global__ void __launch_bounds__(32 * kEmitWarps) emit_frames_kernel(const EmitParams p, const uint32_t *counters,
+                                                                      const uint32_t n_ctas)
+{
+    __shared__ uint16_t s_mag[kEmitWarps][288];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t total = min(counters[C_FRAMES], p.cap);
+    const uint32_t nwarps = gridDim.x * kEmitWarps;
+    for (uint32_t f = blockIdx.x * kEmitWarps + warp; f < total; f += nwarps) {
+        // resolve block whose exclusive prefix is the last one <= f
+        uint32_t lo = 0, hi = n_ctas;           // invariant: cta_excl[lo] <= f, (hi == n_ctas or cta_excl[hi] > f)
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.cta_excl[mid] <= f)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t blk = lo, rel = f - p.cta_excl[blk];
+        const uint32_t t_l = blk * 32 + (uint32_t)lane;
+        const uint32_t c_l = t_l < p.n_tiles ? p.tile_cnt[t_l] : 0u;
+        uint32_t incl = c_l;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        const unsigned owner = __ballot_sync(0xffffffffu, rel >= incl - c_l && rel < incl);
+        const int wl = __ffs(owner) - 1;        // exactly one lane owns rel (rel < block total)
+        const uint32_t tile = blk * 32 + (uint32_t)wl;
+        const uint32_t i = rel - __shfl_sync(0xffffffffu, incl - c_l, wl);
+        const uint2 d = p.tile_dir[tile];
+        const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
+        const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
+        int prev_len = 0;
+        const uint32_t *prev = (FROM_MAG || p.msgs) ? nullptr
+                                                    : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
+        const uint32_t inf = p.emit_info[d.x + i];
+        const uint32_t j = p.rec[6ull * (d.x + ((inf >> 4) & 0x1fffu))];
+        const int t = 4 + (int)(inf & 7u), flen = (inf & 8u) ? 14 : 7;
+        uint32_t words[4] = {0, 0, 0, 0};
+        if (p.msgs == nullptr) {
+            for (int k = lane; k < 288; k += 32) {      // magnitudes of data[j+19 .. j+19+288)
+                const int idx = (int)j + 19 + k;
+                uint32_t m = 0;
+                if (FROM_MAG) {
+                    const uint16_t *dd = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
+                    if (idx < kMagLen)
+                        m = dd[idx];
+                } else {
+                    const uint32_t *bb = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
+                    m = mag_bits_fast(iq_word(bb, idx - kTrailing, len, prev, prev_len)) & 0xffffu;   // == mag_pair
+                }
+                s_mag[warp][k] = (uint16_t)m;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int wi = 0; wi < 4; wi++) {
+                const int n = 32 * wi + lane;
+                bool one = false;
+                if (n < 112) {
+                    const int P = t + 12 * n;          // relative to 5*(j+19)
+                    const int i5 = P / 5, phi = P - 5 * i5;
+                    const uint16_t *m = &s_mag[warp][i5];
+                    const int m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3];
+                    int x;
+                    switch (phi) {                      // demod_2400.rs:72-83
+                    case 0: x = 5 * m0 - 3 * m1 - 2 * m2; break;
+                    case 1: x = 4 * m0 - m1 - 3 * m2; break;
+                    case 2: x = 3 * m0 + m1 - 4 * m2; break;
+                    case 3: x = 2 * m0 + 3 * m1 - 5 * m2; break;
+                    default: x = m0 + 5 * m1 - 5 * m2 - m3; break;
+                    }
+                    one = x > 0;
+                }
+                words[wi] = __ballot_sync(0xffffffffu, one);
+            }
+            __syncwarp();
+        }
+        uint8_t by[16];
+#pragma unroll
+        for (int kb = 0; kb < 14; kb++) {
+            uint32_t v;
+            if (p.msgs)
+                v = p.msgs[14ull * ((unsigned long long)b * 1024ull + j) + kb];
+            else
+                v = __brev((words[kb >> 2] >> (8 * (kb & 3))) & 0xffu) >> 24;
+            by[kb] = (kb < flen) ? (uint8_t)v : (uint8_t)0;
+        }
+        by[14] = (uint8_t)flen;
+        by[15] = (uint8_t)t;
+        if (lane == 0) {
+            uint32_t *o = reinterpret_cast<uint32_t *>(p.out + f);
+#pragma unroll
+            for (int wq = 0; wq < 4; wq++)
+                o[wq] = by[4 * wq] | (by[4 * wq + 1] << 8) | (by[4 * wq + 2] << 16) | ((uint32_t)by[4 * wq + 3] << 24);
+            o[4] = (inf >> 17) & 0x7fffu;   // score (>= 0 here), reserved = 0
+            o[5] = j;
+            o[6] = b;
+        }
+    }
+}
+
 // Small batches (one SDR read per call): the whole second stage in one launch of one block --
 // finalise, resolve, scan, emit, commit -- because five dependent launches of a few
 // microseconds each would dominate the call.
