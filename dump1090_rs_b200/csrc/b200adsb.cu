@@ -62,7 +62,8 @@ struct b200adsb_ctx {
     uint16_t *d_mag8 = nullptr;      // v8 intermediates for one chunk of buffers
     uint32_t *d_planes8 = nullptr;
     size_t v8_cb = 0;                // buffers the intermediates hold
-    int v8_spb = -1, v8_chunk = 0;   // v8_chunk: buffers per dense/sparse launch pair (0: the whole batch)
+    int v8_spb = -1, v8_chunk = 0;
+    bool counters_clean = false;     // C_POOL/C_FLAGS/C_CAND already zero (cleared by the last commit kernel)   // v8_chunk: buffers per dense/sparse launch pair (0: the whole batch)
     uint32_t *d_scalar = nullptr;
 
     uint32_t *d_rec = nullptr, *d_emit_info = nullptr;
@@ -423,6 +424,10 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
 
 int reset_scan_counters(b200adsb_ctx *c)
 {
+    if (c->counters_clean) {   // the previous (enqueue-only) batch cleared them on the device
+        c->counters_clean = false;
+        return B200ADSB_OK;
+    }
     // C_POOL, C_FLAGS cleared; C_CAND cleared; filter-full flag is per batch too
     CK(c, cudaMemsetAsync(c->d_counters + C_POOL, 0, 8, c->stream));
     CK(c, cudaMemsetAsync(c->d_counters + C_CAND, 0, 4, c->stream));
@@ -553,7 +558,7 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     ep.cap = (uint32_t)std::min<size_t>(cap, 0xffffffffu);
     ep.msgs = q.msgs;
     const bool save_tail = c->carry && !q.from_mag && !q.msgs && q.n_buffers > 0;
-    const bool small = n_ctas <= 16 && !d_per_buffer_counts;
+    const bool small = n_ctas <= 16 && !d_per_buffer_counts && !d_async_result;
     if (small) {
         // one launch for the whole second stage (the tail is saved first: commit ends the kernel)
         if (save_tail) {
@@ -572,12 +577,13 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
         events_finalize_kernel<<<1, 1024, 0, c->stream>>>(fa);
         CK(c, cudaGetLastError());
         if (q.n_tiles) {
-            resolve_kernel<<<n_ctas, kResolveThreads, 0, c->stream>>>(rp);
+            // the last block also scans the per-block sums (32 tiles each); total -> counters[C_FRAMES]
+            resolve_kernel<<<n_ctas, kResolveThreads, 0, c->stream>>>(rp, c->d_counters);
+            CK(c, cudaGetLastError());
+        } else {
+            tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_cta_sum, n_ctas, c->d_counters);
             CK(c, cudaGetLastError());
         }
-        // exclusive scan over the per-block sums (32 tiles each); total -> counters[C_FRAMES]
-        tile_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_cta_sum, n_ctas, c->d_counters);
-        CK(c, cudaGetLastError());
         if (d_per_buffer_counts && q.n_buffers) {
             buffer_counts_kernel<<<(q.n_buffers + 255) / 256, 256, 0, c->stream>>>(
                 c->d_tile_emit, q.n_buffers, q.tpb, d_per_buffer_counts);
@@ -600,15 +606,15 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
             CK(c, cudaGetLastError());
         }
         events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
-                                                        c->d_new_keys, c->d_counters, c->d_members);
+                                                        c->d_new_keys, c->d_counters, c->d_members,
+                                                        d_async_result, ep.cap);
         CK(c, cudaGetLastError());
-        c->timing.other_launches += 5;
+        c->timing.other_launches += 4;
     }
     if (d_async_result) {
-        // enqueue-only form: the batch outcome stays on the device, nothing is read back here
-        batch_result_kernel<<<1, 32, 0, c->stream>>>(c->d_counters, d_async_result, ep.cap);
-        CK(c, cudaGetLastError());
-        c->timing.other_launches++;
+        // enqueue-only form: the batch outcome stays on the device (written by the commit kernel, which
+        // also cleared the per-batch counters), nothing is read back here
+        c->counters_clean = !small;
         prof_end(c, c->other_events);
         q.active = false;
         if (save_tail)

@@ -69,7 +69,7 @@ constexpr uint32_t kNoneMarker = 1;  // kind NONE, key 1: score_modes_message re
 
 // counters block (device, u32)
 enum { C_POOL = 0, C_FLAGS = 1, C_EV_USED = 2, C_FRAMES = 3, C_CAND = 4, C_MEMBERS = 5,
-       C_ADMIT = 6, C_NEWCNT = 7, C_WORDS = 16 };
+       C_ADMIT = 6, C_NEWCNT = 7, C_TICKET = 8, C_WORDS = 16 };
 enum : uint32_t { F_POOL_OVF = 1, F_EV_OVF = 2, F_FILTER_FULL = 4 };
 
 constexpr uint32_t kMemberSlots = 8192;   // open addressing, >= 2 x 4096 keys
@@ -1243,11 +1243,23 @@ __device__ __forceinline__ void events_commit_body(uint32_t *ev_keys, unsigned l
         counters[C_NEWCNT] = 0;
     }
 }
+// d_result (nullable): the enqueue-only batch outcome {frames, overflow flags, candidates,
+// frames > cap}; the per-batch counters are then cleared here instead of by host memsets
 __global__ void __launch_bounds__(1024) events_commit_kernel(uint32_t *ev_keys, unsigned long long *ev_ord,
                                                              const uint32_t *ev_used, const uint32_t *new_keys,
-                                                             uint32_t *counters, uint32_t *members)
+                                                             uint32_t *counters, uint32_t *members,
+                                                             uint32_t *d_result = nullptr, uint32_t cap = 0)
 {
     events_commit_body(ev_keys, ev_ord, ev_used, new_keys, counters, members);
+    if (d_result && threadIdx.x == 0) {
+        d_result[0] = counters[C_FRAMES];
+        d_result[1] = counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF);
+        d_result[2] = counters[C_CAND];
+        d_result[3] = counters[C_FRAMES] > cap ? 1u : 0u;
+        counters[C_POOL] = 0;
+        counters[C_FLAGS] = 0;
+        counters[C_CAND] = 0;
+    }
 }
 
 // ================================================================== resolve
@@ -1347,9 +1359,23 @@ __device__ __forceinline__ void resolve_body(const ResolveParams &p, const uint3
     }
     __syncthreads();   // s_cnt is reused by the next block of tiles in the fused small-batch kernel
 }
-__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const ResolveParams p)
+__device__ __forceinline__ void tile_scan_body(uint32_t *tile_emit, uint32_t n_tiles, uint32_t *counters);
+// the last block to finish scans the per-block sums (saves a dependent launch)
+__global__ void __launch_bounds__(kResolveThreads) resolve_kernel(const ResolveParams p, uint32_t *counters)
 {
+    __shared__ uint32_t s_last;
     resolve_body(p, blockIdx.x);
+    if (threadIdx.x == 0) {
+        __threadfence();                                  // cta_sum[blk] before the ticket
+        s_last = atomicAdd(&counters[C_TICKET], 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        tile_scan_body(p.cta_sum, gridDim.x, counters);   // -> exclusive prefix, counters[C_FRAMES]
+        if (threadIdx.x == 0)
+            counters[C_TICKET] = 0;
+    }
 }
 
 // exclusive scan of tile_emit (in place) by one block; total -> counters[C_FRAMES];
@@ -1364,7 +1390,7 @@ __device__ __forceinline__ void tile_scan_body(uint32_t *tile_emit, uint32_t n_t
     __syncthreads();
     for (uint32_t base = 0; base < n_tiles; base += 1024) {
         const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_tiles ? tile_emit[i] : 0u;
+        const uint32_t v = i < n_tiles ? *reinterpret_cast<volatile uint32_t *>(tile_emit + i) : 0u;
         uint32_t incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -1707,17 +1733,6 @@ __global__ void save_tail_kernel(const uint32_t *in, unsigned long long stride, 
 }
 
 // ================================================================== filter helpers
-// outcome of an enqueue-only batch: {frames, flags, candidates, frames > cap}
-__global__ void batch_result_kernel(const uint32_t *counters, uint32_t *out, uint32_t cap)
-{
-    if (threadIdx.x == 0) {
-        out[0] = counters[C_FRAMES];
-        out[1] = counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF);
-        out[2] = counters[C_CAND];
-        out[3] = counters[C_FRAMES] > cap ? 1u : 0u;
-    }
-}
-
 __global__ void filter_add_kernel(uint32_t *members, uint32_t *counters, uint32_t key)
 {
     if (threadIdx.x || blockIdx.x)
