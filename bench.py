@@ -239,6 +239,11 @@ def main() -> int:
             step_no[0] += 1
         elif world == 1:
             n_frames[0] = ctx.demod_iq_batch_ptr(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap)
+        elif use_async[0]:
+            sh.position = 0
+            sh.step_async(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap,
+                          results[step_no[0] % results.shape[0]].data_ptr())
+            step_no[0] += 1
         else:
             # scan -> all-gather of ICAO add-events (NCCL) -> resolve
             sh.position = 0
@@ -253,7 +258,7 @@ def main() -> int:
         step_device()
     barrier()
     ctx.timing(reset=True)
-    use_async[0] = (world == 1) and not args.sync_steps
+    use_async[0] = not args.sync_steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         barrier()
@@ -368,9 +373,10 @@ def main() -> int:
                        "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES, "injected_msgs": args.msgs, "injected_in_all_buffers": bool(args.msgs_all),
                        "l2": f"inputs {nb * SAMPLES * 4 / 2**20:.0f} MiB per GPU > 126 MB L2 (no flush needed)",
                        "frames_per_step": n_frames[0],
-                       "step_call": ("b200adsb_demod_iq_batch_dev (synchronous, one host round trip per step)"
-                                     if (world > 1 or args.sync_steps) else
-                                     "b200adsb_demod_iq_batch_dev_async (steps queued back to back, outcomes checked after the timed region)")},
+                       "step_call": ("synchronous ABI calls (host round trips inside every step)" if args.sync_steps else
+                                     ("b200adsb_demod_iq_batch_dev_async" if world == 1 else
+                                      "b200adsb_scan_batch_dev_async + events all-gather + b200adsb_resolve_batch_dev_async")
+                                     + " (steps queued back to back, outcomes checked after the timed region)")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(tim["scan_launches"] + tim["other_launches"]),
             "clocks": clk.summary(),

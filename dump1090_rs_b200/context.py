@@ -144,6 +144,16 @@ class Context:
                                                     lengths_ptr or None, first_ordinal, ordinal_stride),
                     "scan_batch_dev")
 
+    def scan_batch_dev_async(self, iq_ptr: int, n_buffers: int, spb: int, stride: int, first_ordinal: int,
+                             ordinal_stride: int, lengths_ptr: int = 0):
+        self._check(self._L.b200adsb_scan_batch_dev_async(self._h, iq_ptr, n_buffers, spb, stride,
+                                                          lengths_ptr or None, first_ordinal, ordinal_stride),
+                    "scan_batch_dev_async")
+
+    def resolve_batch_dev_async(self, out_ptr: int, cap: int, result_ptr: int):
+        self._check(self._L.b200adsb_resolve_batch_dev_async(self._h, out_ptr, cap, result_ptr),
+                    "resolve_batch_dev_async")
+
     def events_count(self) -> int:
         n = C.c_size_t(0)
         self._check(self._L.b200adsb_events_count(self._h, C.byref(n)), "events_count")

@@ -915,6 +915,35 @@ int b200adsb_scan_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffe
     return rc;
 }
 
+// enqueue-only forms of the sharded pair (see b200adsb_demod_iq_batch_dev_async)
+int b200adsb_scan_batch_dev_async(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffers, size_t spb,
+                                  size_t stride, const uint32_t *d_lengths, uint64_t first_ordinal,
+                                  uint64_t ordinal_stride)
+{
+    if (!c || (!d_iq && n_buffers && spb) || (stride < spb && n_buffers > 1))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    rc = scan_begin(c, d_iq, false, n_buffers, spb, stride, d_lengths, first_ordinal,
+                    ordinal_stride ? ordinal_stride : 1);
+    if (rc) return rc;
+    rc = reset_scan_counters(c);
+    if (!rc)
+        rc = launch_scan(c, 0, c->cur.n_buffers);
+    if (rc)
+        c->cur.active = false;
+    return rc;
+}
+
+int b200adsb_resolve_batch_dev_async(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, uint32_t *d_result)
+{
+    if (!c || (!d_out && cap) || !d_result)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    return resolve_run(c, d_out, cap, nullptr, nullptr, d_result);
+}
+
 int b200adsb_events_count(b200adsb_ctx *c, size_t *n)
 {
     if (!c || !n)

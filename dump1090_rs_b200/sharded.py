@@ -84,3 +84,20 @@ class ShardedDemodulator:
         n = self.ctx.resolve_batch_dev(out_ptr, cap, counts_ptr)
         self.position += n_total
         return n
+
+    def step_async(self, iq_ptr: int, n_local: int, spb: int, stride: int, out_ptr: int, cap: int,
+                   result_ptr: int, n_total: int | None = None) -> None:
+        """Enqueue-only step: scan, event exchange and resolve are queued on the context's stream
+        (which must be torch's current stream, so that the NCCL all-gather is ordered with them);
+        the outcome {frames, overflow flags, candidates, frames > cap} lands in result_ptr
+        (4 x uint32 on the device).  Batches execute in call order."""
+        import torch.distributed as dist
+
+        n_total = n_local * self.world if n_total is None else n_total
+        self.ctx.scan_batch_dev_async(iq_ptr, n_local, spb, stride, self.position + self.rank, self.world)
+        if self.world > 1:
+            self.ctx.events_pack_dev(self.rows.data_ptr(), self.event_rows)
+            dist.all_gather_into_tensor(self.gathered, self.rows, group=self.group)
+            self.ctx.events_import_packed_dev(self.gathered.data_ptr(), self.world, self.event_rows, self.rank)
+        self.ctx.resolve_batch_dev_async(out_ptr, cap, result_ptr)
+        self.position += n_total

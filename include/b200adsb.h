@@ -184,6 +184,16 @@ int b200adsb_events_import_packed_dev(b200adsb_ctx *ctx, const uint64_t *d_gathe
 int b200adsb_resolve_batch_dev(b200adsb_ctx *ctx, b200adsb_frame *d_out, size_t cap,
                                size_t *n_out, uint32_t *d_per_buffer_counts);
 
+/* enqueue-only forms (no host round trip; outcome in d_result as for
+ * b200adsb_demod_iq_batch_dev_async): scan_async -> events_pack -> all-gather ->
+ * events_import_packed -> resolve_async, all on the context's stream */
+int b200adsb_scan_batch_dev_async(b200adsb_ctx *ctx, const int16_t *d_iq, size_t n_buffers,
+                                  size_t samples_per_buffer, size_t stride_samples,
+                                  const uint32_t *d_lengths, uint64_t first_ordinal,
+                                  uint64_t ordinal_stride);
+int b200adsb_resolve_batch_dev_async(b200adsb_ctx *ctx, b200adsb_frame *d_out, size_t cap,
+                                     uint32_t *d_result);
+
 /* --------------------------------------------------------------- icao_filter.rs */
 int b200adsb_icao_flush(b200adsb_ctx *ctx);                    /* icao_flush       :11-17 */
 uint32_t b200adsb_icao_hash(uint32_t a);                       /* icao_hash        :19-43 */
