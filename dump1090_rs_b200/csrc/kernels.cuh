@@ -1304,27 +1304,32 @@ __device__ __forceinline__ void resolve_body(const ResolveParams &p, const uint3
         const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
         const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
         for (uint32_t i = lane; i < d.y; i += 32) {
-            const uint32_t *r = p.rec + 6ull * (d.x + i);
-            const uint32_t j = r[0];
+            // one 24-byte record = three aligned 8-byte loads; the five words are scored without a
+            // branch per word (lanes hold different kinds: a switch here ran at 14 of 32 lanes)
+            const uint2 *r2 = reinterpret_cast<const uint2 *>(p.rec + 6ull * (d.x + i));
+            const uint2 ra = r2[0], rb = r2[1], rc = r2[2];
+            const uint32_t j = ra.x;
+            const uint32_t w5[5] = {ra.y, rb.x, rb.y, rc.x, rc.y};
             int best = -2;                        // demod_2400.rs:152
             uint32_t best_t = 0, best_len = 7;
 #pragma unroll
             for (int tt = 0; tt < 5; tt++) {
-                const uint32_t wd = r[1 + tt];
+                const uint32_t wd = w5[tt];
                 const uint32_t kind = wd >> 29, key = wd & 0xffffffu;
+                // membership: address 0 always tests true (icao_filter.rs:71,78); the bloom word
+                // rejects almost every other key with one load
+                bool m = key == 0u;
+                if (kind != K_NONE && key != 0u && bloom_hit(p.bloom, key))
+                    m = members_has(p.members, key) ||
+                        event_first(p.ev_keys, p.ev_ord, p.ev_mask, key) < (ord_buf | ((unsigned long long)j << 3) | (unsigned)tt);
+                // mode_s/mod.rs:56-134 as selects: (member, not member) scores and the frame length
+                const bool df1718 = kind == K_DF17 || kind == K_DF18;
+                const int s_m = kind == K_DF11_IID0 ? 1600 : (df1718 ? 1800 : 1000);
+                const int s_n = kind == K_DF11_IID0 ? 750 : (df1718 ? 1400 : (kind == K_PAR_LONG ? -2 : -1));
+                int score = m ? s_m : s_n;
                 if (kind == K_NONE)
-                    continue;
-                const bool m = is_member(p, key, ord_buf | ((unsigned long long)j << 3) | (unsigned)tt);
-                int score;
-                uint32_t len;
-                switch (kind) {                   // mode_s/mod.rs:56-134
-                case K_PAR_SHORT: score = m ? 1000 : -1; len = 7; break;
-                case K_DF11_IID0: score = m ? 1600 : 750; len = 7; break;
-                case K_DF11_IID: score = m ? 1000 : -1; len = 7; break;
-                case K_DF17:
-                case K_DF18: score = m ? 1800 : 1400; len = 14; break;
-                default: score = m ? 1000 : -2; len = 14; break;
-                }
+                    score = -3;                   // None / rejected statelessly: never beats -2
+                const uint32_t len = (df1718 || kind == K_PAR_LONG) ? 14u : 7u;
                 if (score > best) {               // demod_2400.rs:185 (strict)
                     best = score;
                     best_t = (uint32_t)tt;
@@ -1590,14 +1595,17 @@ __global__ void __launch_bounds__(32 * kEmitWarps) emit_frames_kernel(const Emit
     const uint32_t total = min(counters[C_FRAMES], p.cap);
     const uint32_t nwarps = gridDim.x * kEmitWarps;
     for (uint32_t f = blockIdx.x * kEmitWarps + warp; f < total; f += nwarps) {
-        // resolve block whose exclusive prefix is the last one <= f
-        uint32_t lo = 0, hi = n_ctas;           // invariant: cta_excl[lo] <= f, (hi == n_ctas or cta_excl[hi] > f)
-        while (hi - lo > 1) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (p.cta_excl[mid] <= f)
-                lo = mid;
-            else
-                hi = mid;
+        // resolve block whose exclusive prefix is the last one <= f: 32-ary search, one probe per lane
+        // (two dependent loads for up to 1024 blocks instead of ten)
+        uint32_t lo = 0, span = n_ctas;         // the answer lies in [lo, lo + span)
+        while (span > 1) {
+            const uint32_t stp = (span + 31) / 32;
+            const uint32_t idx = lo + (uint32_t)lane * stp;
+            const bool le = idx < lo + span && p.cta_excl[idx] <= f;
+            const int seg = __popc(__ballot_sync(0xffffffffu, le)) - 1;   // lane 0 always holds (cta_excl[lo] <= f)
+            const uint32_t nlo = lo + (uint32_t)seg * stp;
+            span = min(stp, lo + span - nlo);
+            lo = nlo;
         }
         const uint32_t blk = lo, rel = f - p.cta_excl[blk];
         const uint32_t t_l = blk * 32 + (uint32_t)lane;
