@@ -468,22 +468,33 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 base = (int)atomicAdd(&s_count, (uint32_t)incl);
             base = __shfl_sync(0xffffffffu, base, 31);
             int off = base + incl - cnt;
-            const int mi0 = 12 * 32 * w + rho;
             uint32_t any = m.x;
             while (any) {
                 const int bit = __ffs(any) - 1;
                 any &= any - 1;
-                if (off < k7ListCap) {
+                if (off < k7ListCap)
                     list[off] = (uint16_t)(i | (bit << 10));       // (mask word, bit); the gate thread decodes
-                } else {                                            // list full: evaluate in place (out of line)
-                    const uint32_t cs = ((m.y >> bit) & 1u) | (((m.z >> bit) & 1u) << 1) | (((m.w >> bit) & 1u) << 2);
-                    gate_eval7_cold(mag, surv, mi0 + 12 * bit, cs, npos);
-                }
                 off++;
             }
         }
     }
     __syncthreads();
+    if (s_count > (uint32_t)k7ListCap) {
+        // more matches than the list holds (pathological input): gate every match in place.  Matches
+        // that also made it into the list are evaluated twice, which is harmless (a gate only sets a bit).
+        const uint4 *min4 = reinterpret_cast<const uint4 *>(masks);
+        for (int i = tid; i < 12 * P.Wrow; i += k7Threads) {
+            const int rho = (int)(((uint32_t)i * (uint32_t)P.inv_Wrow) >> 16), w = i - rho * P.Wrow;
+            if (w >= nwq)
+                continue;
+            const uint4 m = min4[i];
+            for (uint32_t any = m.x; any; any &= any - 1) {
+                const int bit = __ffs(any) - 1;
+                const uint32_t cs = ((m.y >> bit) & 1u) | (((m.z >> bit) & 1u) << 1) | (((m.w >> bit) & 1u) << 2);
+                gate_eval7_cold(mag, surv, 12 * (32 * w + bit) + rho, cs, npos);
+            }
+        }
+    }
     // ---- P3c: SNR and quiet-zone gates, one match per thread
     {
         const uint4 *min4 = reinterpret_cast<const uint4 *>(masks);

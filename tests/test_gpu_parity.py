@@ -522,3 +522,30 @@ def test_enqueue_only_batches_match_synchronous_calls(pkg):
     assert c_q == c_sync
     assert f_q == f_sync
     assert s_q == s_sync
+
+
+def test_dense_template_matches_overflow_the_match_list(pkg, ctx, oracle_mod):
+    """A periodic magnitude pattern on which 3 of every 11 positions match a preamble template AND
+    pass the SNR / quiet-zone gates (~2000 matches and survivors per tile: twice the capacity of the
+    kernel's match list, 16 decode windows per tile, a candidate pool that has to grow): frames and
+    the number of surviving positions must be the oracle's.  The rest of the buffer is noise with
+    injected messages."""
+    from dump1090_rs_b200 import synth
+    pat = np.array([3, 8, 11, 4, 11, 1, 4, 9, 8, 1, 11])
+    n = 131072
+    iq = synth.make_batch(5, 1, msgs_per_buffer=20)[0].copy()
+    part = n // 4
+    levels = np.tile(pat, part // len(pat) + 1)[:part]
+    iq[:part, 0] = (250 * levels + 100).astype(np.int16)
+    iq[:part, 1] = 0
+    orc = oracle_mod.Oracle()
+    mb = orc.to_mag(iq)
+    n_surv = len(orc.records(mb, cap=1 << 17))
+    assert n_surv > 0.2 * part            # the premise: the pattern is dense in survivors
+    ref = orc.demod_iq(iq, flush=True)
+    ctx.icao_flush()
+    ctx.timing(reset=True)
+    got = ctx.demod_iq(iq)
+    assert frames_key(got) == frames_key(ref)
+    assert len(ref) > 0
+    assert ctx.timing()["candidates"] == n_surv
