@@ -283,7 +283,7 @@ def main() -> int:
     value = total_samples * args.steps / (ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (scan): algorithmic bytes = 4 B per IQ sample
-    SCAN_KERNEL = {"6": "scan_kernel<false>", "8": "dense8_kernel<false> + sparse8_kernel"}.get(
+    SCAN_KERNEL = {"6": "scan_kernel<false>"}.get(
         os.environ.get("B200ADSB_SCAN", "7"), "scan7_kernel<false>")
     peak, peak_src = peaks()
     # (the scan kernel is launched once per chunk of tiles; sum over the timed region)

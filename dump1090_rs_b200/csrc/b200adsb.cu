@@ -15,7 +15,6 @@
 
 #include "kernels.cuh"
 #include "scan7.cuh"
-#include "scan8.cuh"
 
 using namespace b200;
 
@@ -58,12 +57,8 @@ struct b200adsb_ctx {
     uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr, *d_lut = nullptr;
     uint32_t h_lut[kLutWords];
     int lut_T = 0, lut_WP = 0;
-    int scan_ver = 7;   // stage-1 kernel generation (B200ADSB_SCAN=6/7/8 for A/B runs; 8 = dense + sparse kernels)
-    uint16_t *d_mag8 = nullptr;      // v8 intermediates for one chunk of buffers
-    uint32_t *d_planes8 = nullptr;
-    size_t v8_cb = 0;                // buffers the intermediates hold
-    int v8_spb = -1, v8_chunk = 0;
-    bool counters_clean = false;     // C_POOL/C_FLAGS/C_CAND already zero (cleared by the last commit kernel)   // v8_chunk: buffers per dense/sparse launch pair (0: the whole batch)
+    int scan_ver = 7;   // stage-1 kernel generation (B200ADSB_SCAN=6 selects the previous one for A/B runs)
+    bool counters_clean = false;     // C_POOL/C_FLAGS/C_CAND already zero (cleared by the last commit kernel)
     uint32_t *d_scalar = nullptr;
 
     uint32_t *d_rec = nullptr, *d_emit_info = nullptr;
@@ -298,8 +293,7 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.crc_tabs = c->d_crc_tabs;
     ScanSmem L(q.T);
     Scan7Smem L7(q.T);
-    const Scan8Geom G8((int)q.spb);
-    const int WPsel = c->scan_ver == 8 ? G8.WQ : (c->scan_ver >= 7 ? L7.WP : L.WP);
+    const int WPsel = c->scan_ver >= 7 ? L7.WP : L.WP;
     if (c->lut_T != q.T || c->lut_WP != WPsel) {
         // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
         // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream in
@@ -333,53 +327,6 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     const uint32_t grid = nb * (uint32_t)q.tpb;
     if (grid == 0)
         return B200ADSB_OK;
-    if (c->scan_ver == 8) {
-        const size_t cb_max = c->v8_chunk > 0 ? std::min<size_t>((size_t)c->v8_chunk, nb) : nb;
-        if (c->v8_cb < cb_max || c->v8_spb != (int)q.spb) {
-            CK(c, cudaStreamSynchronize(c->stream));
-            cudaFree(c->d_mag8);
-            cudaFree(c->d_planes8);
-            c->d_mag8 = nullptr;
-            c->d_planes8 = nullptr;
-            c->v8_cb = 0;
-            const size_t mag_b = cb_max * (size_t)G8.MS * 2, pl_b = cb_max * (size_t)84 * G8.WQ * 4;
-            if (cudaMalloc((void **)&c->d_mag8, mag_b) != cudaSuccess ||
-                cudaMalloc((void **)&c->d_planes8, pl_b) != cudaSuccess) {
-                snprintf(c->err, sizeof(c->err), "stage-1 intermediates (%zu buffers)", cb_max);
-                return B200ADSB_ERR_NOMEM;
-            }
-            CK(c, cudaMemsetAsync(c->d_mag8, 0, mag_b, c->stream));
-            CK(c, cudaMemsetAsync(c->d_planes8, 0, pl_b, c->stream));   // pad words stay zero for ever
-            c->v8_cb = cb_max;
-            c->v8_spb = (int)q.spb;
-        }
-        Scan8Params P8;
-        P8.s = p;
-        P8.magG = c->d_mag8;
-        P8.planesG = c->d_planes8;
-        P8.NGb = G8.NGb;
-        P8.WQ = G8.WQ;
-        P8.MS = G8.MS;
-        P8.nblk = G8.nblk;
-        P8.nW = q.T / 384;
-        const Sparse8Smem S8(P8.nW);
-        CK(c, cudaFuncSetAttribute(sparse8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S8.bytes));
-        prof_begin(c, c->scan_events);
-        for (size_t cb0 = 0; cb0 < nb; cb0 += cb_max) {
-            const uint32_t cb = (uint32_t)std::min<size_t>(cb_max, nb - cb0);
-            P8.b_off = (uint32_t)cb0;
-            if (q.from_mag)
-                dense8_kernel<true><<<cb * (uint32_t)G8.nblk, k7Threads, 0, c->stream>>>(P8);
-            else
-                dense8_kernel<false><<<cb * (uint32_t)G8.nblk, k7Threads, 0, c->stream>>>(P8);
-            sparse8_kernel<<<cb * (uint32_t)q.tpb, k7Threads, S8.bytes, c->stream>>>(P8);
-        }
-        prof_end(c, c->scan_events);
-        CK(c, cudaGetLastError());
-        c->timing.scan_launches++;
-        c->timing.samples += (uint64_t)nb * q.spb;
-        return B200ADSB_OK;
-    }
     prof_begin(c, c->scan_events);
     if (c->scan_ver >= 7) {
         Scan7Params P7;
@@ -460,17 +407,8 @@ int scan_begin(b200adsb_ctx *c, const void *d_in, bool from_mag, size_t n_buffer
     q.n_buffers = (uint32_t)n_buffers;
     q.spb = (uint32_t)spb;
     q.stride = stride;
-    if (c->scan_ver == 8) {
-        // sparse tiles are whole word columns of the mod-12 planes: T = 384 * nW positions
-        int nW = k8MaxCols;
-        while (nW > 1 && n_buffers * ((spb + kHaloFront + 384 * (size_t)nW - 1) / (384 * (size_t)nW)) < 592)
-            nW >>= 1;
-        q.T = 384 * nW;
-        q.tpb = spb ? (int)((spb + kHaloFront + q.T - 1) / q.T) : 0;
-    } else {
-        q.T = pick_tile(c, n_buffers, spb);
-        q.tpb = spb ? (int)((spb + q.T - 1) / q.T) : 0;
-    }
+    q.T = pick_tile(c, n_buffers, spb);
+    q.tpb = spb ? (int)((spb + q.T - 1) / q.T) : 0;
     q.n_tiles = (uint32_t)(n_buffers * (size_t)q.tpb);
     q.ord_first = ord_first;
     q.ord_stride = ord_stride;
@@ -718,9 +656,7 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     } while (0)
     CKC(cudaSetDevice(device));
     if (const char *sv = getenv("B200ADSB_SCAN"))
-        c->scan_ver = atoi(sv) == 6 ? 6 : (atoi(sv) == 8 ? 8 : 7);
-    if (const char *sv = getenv("B200ADSB_CHUNK"))
-        c->v8_chunk = atoi(sv);
+        c->scan_ver = atoi(sv) == 6 ? 6 : 7;
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -781,8 +717,6 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_crc_tabs);
     cudaFree(c->d_crc256);
     cudaFree(c->d_lut);
-    cudaFree(c->d_mag8);
-    cudaFree(c->d_planes8);
     cudaFree(c->d_scalar);
     cudaFree(c->d_rec);
     cudaFree(c->d_emit_info);

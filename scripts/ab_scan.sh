@@ -1,7 +1,7 @@
 #!/bin/bash
-# A/B of the stage-1 kernel generations on one box: scripts/ab_scan.sh ROUNDS VER...   (VER = 6, 7, 8 or 8:CHUNK)
+# A/B of the stage-1 kernel generations on one box: scripts/ab_scan.sh ROUNDS VER...   (VER = 6 or 7)
 rounds=${1:-2}; shift
-vers=${@:-6 7 8}
+vers=${@:-6 7}
 for round in $(seq 1 $rounds); do
   for v in $vers; do
     ver=${v%%:*}; chunk=0; [[ $v == *:* ]] && chunk=${v##*:}
