@@ -1,24 +1,27 @@
 // dump1090_rs_b200/csrc/kernels.cuh -- device side of libb200adsb (sm_100a).
 //
 // The reference scans one sample at a time on one CPU thread
-// (src/demod_2400.rs:115-212).  Here the same arithmetic is re-organised for a
-// GPU:
+// (src/demod_2400.rs:115-212).  Here the same arithmetic is re-organised for a GPU.
+// This file holds what both generations of the stage-1 kernel share (exact fast magnitude,
+// CRC-24 by fields, classification, event table, gates), the previous generation itself
+// (scan_kernel, "v6", selectable with B200ADSB_SCAN=6 for A/B runs; the current one is
+// scan7_kernel in scan7.cuh), stage 2 and the API-parity kernels.
 //
 //   scan_kernel (one thread block per tile of T output positions)
-//     P1  IQ -> u16 magnitude into shared memory            (src/utils.rs:43-58)
-//     P2  every sample's five PPM correlator signs and its rising/falling edge
-//         bits, packed by warp ballots into bit planes that are de-interleaved
-//         modulo 12 samples (= one Mode-S bit period at 2.4 Msps is 12/5
-//         samples, so message bit n of try-phase t lives at 1/5-sample position
-//         P = 5(j+19)+t+12n: sample P/5, correlator P%5)  (src/demod_2400.rs:62-83,158-182)
+//     P1  IQ -> u16 magnitude, edge bits and first differences into shared memory
+//                                                          (src/utils.rs:43-58)
+//     P2  every sample's five PPM correlator signs as bit planes de-interleaved modulo 12
+//         samples (one Mode-S bit period at 2.4 Msps is 12/5 samples, so message bit n of
+//         try-phase t lives at 1/5-sample position P = 5(j+19)+t+12n: sample P/5,
+//         correlator P%5)                                  (src/demod_2400.rs:62-83,158-182)
 //     P3  the five preamble templates evaluated 32 positions at a time as AND/shift
-//         of the edge bit planes, then SNR + quiet-zone gates on the survivors
+//         of the edge bitmaps, then SNR + quiet-zone gates on the matches
 //                                                          (src/demod_2400.rs:127-146,215-321)
 //     P4  per surviving position and try-phase: five 23-bit field extracts from
 //         the planes, DF, CRC-24 syndrome by table (GF(2)-linear), stateless
 //         classification -> one 24-byte record; ICAO add-events by atomicMin
 //                                                          (src/mode_s/mod.rs:34-139, src/crc.rs:263-282)
-//   finalize/resolve/emit kernels
+//   finalize / resolve / emit / commit kernels
 //         the sequential ICAO filter (src/icao_filter.rs) evaluated order-free:
 //         member(a) at ordinal o  <=>  a == 0 || a in filter before the batch ||
 //         firstAdd(a) < o; best-of-5 with the reference's strict '>' rule;

@@ -5,22 +5,25 @@
 //
 // Dense phase.  The halo-extended tile is NG groups of 192 samples.  Three lanes own a group:
 // lane c (0..2) takes, for slot k = 15..0, the four consecutive samples 192G + 12k + 4c + e
-// (one LDG.128 of IQ).  Residue rho = 4c + e of the 12-sample Mode-S bit period is therefore
-// fixed per (lane, e) and slot k is bit k of a 16-bit accumulator: after 16 slots every
-// accumulator IS one halfword of the mod-12 de-interleaved plane[phi][rho] (bit q <-> tile
-// magnitude index 12q + rho), stored with one STS.U16.  The three magnitudes to the right of
-// a row come from lane+1 (c < 2) or from lane-2's previous slot (c == 2) by shuffle.
-// Samples are paired (e, e+2) in the packed f32x2 pipe: the pairs (d0,d2) (d1,d3) (d2,d4)
-// (d3,d5) of first differences serve both correlator pairs without register moves.
+// (one 16-byte IQ row, brought in by cp.async through a per-lane ring).  Residue rho = 4c + e of
+// the 12-sample Mode-S bit period is therefore fixed per (lane, e) and slot k is bit k of a
+// 16-bit accumulator: after 16 slots every accumulator IS one halfword of the mod-12
+// de-interleaved plane[f][rho] (bit q <-> tile magnitude index 12q + rho), stored with one
+// STS.U16.  The three magnitudes to the right of a row come from lane+1 (c < 2) or from
+// lane-2's previous slot (c == 2) by shuffle.  Samples are paired (e, e+2) in the packed f32x2
+// pipe: the pairs (d0,d2) (d1,d3) (d2,d4) (d3,d5) of first differences serve both correlator pairs.
 //   src/utils.rs:43-58 (magnitude), src/demod_2400.rs:62-83 (correlators), :221-317 (edges)
 //
 // Sparse phases.
 //   P3a  one warp, lane = word column, residue static: the five templates as AND of the
-//        rising/falling planes (32 positions at stride 12 per word) -> one match mask per
-//        (template case, rho, word)
-//   P3b  block-wide ordered compaction of the masks into a case-sorted list, then the SNR and
-//        quiet-zone gates one match per thread                       (src/demod_2400.rs:129-146)
-//   P4   as in v6: field extraction from the planes, class-staged CRC-24, records, add-events
+//        rising/falling planes (32 positions at stride 12 per word) -> per (rho, word) the match
+//        mask and the template case as three bit planes
+//   P3b  warps expand 32 mask words per round into one (word, bit) list (warp scan + one shared
+//        atomic per round; order is irrelevant because the gates only set survivor bits)
+//   P3c  SNR and quiet-zone gates, one match per thread, no branch per template case
+//                                                                    (src/demod_2400.rs:129-146)
+//   P4   one warp scans the survivor bitmap; then, as in v6: field extraction from the planes,
+//        class-staged CRC-24, records, ICAO add-events
 #pragma once
 #include "kernels.cuh"
 
