@@ -147,3 +147,117 @@ def test_avr_lines(golden_frames):
     txt = avr.format_frames(frames)
     assert txt == "".join("*%s;\n" % g["hex"] for g in golden_frames[name]).encode()
     assert avr.format_frames([]) == b""
+
+
+# ---------------------------------------------------------------- scan7.cuh (stage-1 kernel v7)
+def _case_of(p):
+    """template case 0..4 of demod_2400.rs:226-317 (first match wins) or -1"""
+    R = [int(p[k] < p[k + 1]) for k in range(13)]
+    F = [int(p[k] > p[k + 1]) for k in range(13)]
+    if not (R[0] & F[12]):
+        return -1
+    T = [F[1] & R[2] & F[3] & R[8] & F[9] & R[10], F[1] & R[2] & F[3] & R[8] & F[9] & R[11],
+         F[1] & R[2] & F[4] & R[8] & F[10] & R[11], F[1] & R[3] & F[4] & R[9] & F[10] & R[11],
+         F[2] & R[3] & F[4] & R[9] & F[10] & R[11]]
+    for cs in range(5):
+        if T[cs]:
+            return cs
+    return -1
+
+
+def test_branch_free_gate_matches_oracle(oracle_mod):
+    """gate_eval_bf (scan7.cuh): the five template cases as selects on the case number give the
+    oracle's SNR / quiet-zone decision (demod_2400.rs:129,135-146 with :226-317)."""
+    rng = np.random.default_rng(11)
+    L = oracle_mod.lib()
+    checked = passed = 0
+    while checked < 3000:
+        # a preamble-like burst so that templates match often, plus random tails
+        base = rng.integers(0, 400, 32)
+        for k in (1, 3, 9, 12) if rng.random() < 0.5 else (1, 4, 10, 12):
+            base[k] += rng.integers(300, 3000)
+        p = base.astype(np.uint16)
+        cs = _case_of(p)
+        if cs < 0:
+            continue
+        a, h, b, e, n5, n6, n7, n8 = (int(p[k]) for k in (1, 2, 3, 4, 5, 6, 7, 8))
+        c, f, g, d = (int(p[k]) for k in (9, 10, 11, 12))
+        bc, ef = b + c, e + f
+        H = a + d + (bc if cs < 3 else 0) + (ef if cs >= 2 else 0) + (g if cs == 0 else 0) + (h if cs == 4 else 0)
+        S = (a if cs < 4 else 0) + (bc if cs < 2 else 0) + (d if cs >= 1 else 0) + (ef if cs >= 3 else 0)
+        N = n6 + n7 + (n5 if (0x0B >> cs) & 1 else 0) + (n8 if (0x1A >> cs) & 1 else 0)
+        mx = max(n5, n6, n7, n8, *(int(p[k]) for k in (14, 15, 16, 17, 18)))
+        model = (2 * S >= 3 * N) and (mx < (H >> 2))
+        data = np.zeros(400, dtype=np.uint16)
+        data[:32] = p
+        assert bool(L.orc_gate(data.ctypes.data, 0)) == model, (cs, p[:19])
+        checked += 1
+        passed += model
+    assert passed > 100          # both outcomes are exercised
+
+
+def test_mod12_plane_templates(oracle_mod):
+    """P3a of scan7.cuh: with the edge bits de-interleaved modulo 12 (plane[rho] bit q <-> index
+    12q + rho), the edge at offset s of position (rho, q) is bit q + (rho+s)//12 of row
+    (rho+s) % 12 -- evaluated word-parallel this gives check_preamble's decision and case."""
+    rng = np.random.default_rng(12)
+    n = 12 * 32 * 3
+    m = rng.integers(0, 30, n + 64).astype(np.int64)
+    for k in rng.integers(0, n - 20, 200):          # sprinkle preamble-like bursts
+        m[k + 1] += 500; m[k + 3] += 500; m[k + 9] += 500; m[k + 12] += 400
+    Rb = (m[:-1] < m[1:]).astype(np.uint64)
+    Fb = (m[:-1] > m[1:]).astype(np.uint64)
+    nq = (n + 64) // 12
+    def plane(bits):
+        rows = []
+        for rho in range(12):
+            v = 0
+            for q in range(nq - 1):
+                v |= int(bits[12 * q + rho]) << q
+            rows.append(v)
+        return rows
+    PR, PF = plane(Rb), plane(Fb)
+    mask = (1 << 64) - 1
+    found = 0
+    for rho in range(12):
+        def X(rows, s):
+            t = rho + s
+            return (rows[t % 12] >> (t // 12)) & mask
+        quick = X(PR, 0) & X(PF, 12)
+        T3 = X(PF, 1) & X(PR, 2) & X(PF, 3) & X(PR, 8) & X(PF, 9) & X(PR, 10)
+        T4 = X(PF, 1) & X(PR, 2) & X(PF, 3) & X(PR, 8) & X(PF, 9) & X(PR, 11)
+        T5 = X(PF, 1) & X(PR, 2) & X(PF, 4) & X(PR, 8) & X(PF, 10) & X(PR, 11)
+        T6 = X(PF, 1) & X(PR, 3) & X(PF, 4) & X(PR, 9) & X(PF, 10) & X(PR, 11)
+        T7 = X(PF, 2) & X(PR, 3) & X(PF, 4) & X(PR, 9) & X(PF, 10) & X(PR, 11)
+        anym = quick & (T3 | T4 | T5 | T6 | T7)
+        c1, c2, c3, c4 = T4 & ~T3, T5 & ~(T3 | T4), T6 & ~(T3 | T4 | T5), ~(T3 | T4 | T5 | T6)
+        b0, b1 = c1 | c3, c2 | c3
+        for q in range(60):
+            i = 12 * q + rho
+            want = _case_of(m[i:i + 14])
+            got = -1
+            if (anym >> q) & 1:
+                got = ((b0 >> q) & 1) | (((b1 >> q) & 1) << 1) | (((c4 >> q) & 1) << 2)
+            assert got == want, (rho, q)
+            found += want >= 0
+    assert found > 20
+
+
+def test_dense_phase_lane_mapping_and_reciprocal():
+    """scan7.cuh dense phase: (group G, lane c, slot k, element e) covers every tile magnitude index
+    exactly once with residue 4c+e and plane bit 16G+k; the host reciprocal used for i / Wrow is
+    exact for every mask-word index."""
+    NG = 40
+    seen = np.zeros(NG * 192, dtype=np.int32)
+    for G in range(NG):
+        for c in range(3):
+            for k in range(16):
+                for e in range(4):
+                    i = 192 * G + 12 * k + 4 * c + e
+                    seen[i] += 1
+                    assert i % 12 == 4 * c + e and i // 12 == 16 * G + k
+    assert (seen == 1).all()
+    for W in range(1, 24):
+        inv = (65536 + W - 1) // W
+        for i in range(12 * W):
+            assert (i * inv) >> 16 == i // W
