@@ -1306,11 +1306,21 @@ __device__ __forceinline__ void resolve_body(const ResolveParams &p, const uint3
         const uint2 d = p.tile_dir[tile];
         const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
         const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
+        // one 24-byte record = three aligned 8-byte loads, fetched one round ahead (the rounds of a
+        // tile are otherwise a chain of dependent DRAM latencies)
+        uint2 na = make_uint2(0u, 0u), nb = na, nc = na;
+        if ((uint32_t)lane < d.y) {
+            const uint2 *r2 = reinterpret_cast<const uint2 *>(p.rec + 6ull * (d.x + (uint32_t)lane));
+            na = r2[0]; nb = r2[1]; nc = r2[2];
+        }
         for (uint32_t i = lane; i < d.y; i += 32) {
-            // one 24-byte record = three aligned 8-byte loads; the five words are scored without a
-            // branch per word (lanes hold different kinds: a switch here ran at 14 of 32 lanes)
-            const uint2 *r2 = reinterpret_cast<const uint2 *>(p.rec + 6ull * (d.x + i));
-            const uint2 ra = r2[0], rb = r2[1], rc = r2[2];
+            // the five words are scored without a branch per word (lanes hold different kinds: a
+            // switch here ran at 14 of 32 lanes)
+            const uint2 ra = na, rb = nb, rc = nc;
+            if (i + 32 < d.y) {
+                const uint2 *r2 = reinterpret_cast<const uint2 *>(p.rec + 6ull * (d.x + i + 32));
+                na = r2[0]; nb = r2[1]; nc = r2[2];
+            }
             const uint32_t j = ra.x;
             const uint32_t w5[5] = {ra.y, rb.x, rb.y, rc.x, rc.y};
             int best = -2;                        // demod_2400.rs:152

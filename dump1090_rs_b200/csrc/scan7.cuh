@@ -41,6 +41,9 @@ constexpr int k7ListCap = 1024;             // template matches gated per round
 #ifndef B200_SCAN7_MIN_BLOCKS
 #define B200_SCAN7_MIN_BLOCKS 7
 #endif
+#ifndef B200_SCAN7_FILL_ALL
+#define B200_SCAN7_FILL_ALL 1               // 1: all warps fill the candidate list (0: warp 0 alone)
+#endif
 #ifndef B200_SCAN7_RING
 #define B200_SCAN7_RING 3                   // IQ rows in flight per lane (cp.async ring); 0: register prefetch
 #endif
@@ -283,6 +286,9 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     const uint32_t *tabs = p.crc_tabs;
     const uint32_t *lut = p.lut;
     __shared__ uint32_t s_base, s_count, s_ok, s_nlong, s_nshort;
+#if B200_SCAN7_FILL_ALL
+    __shared__ uint16_t s_pair_off[k7Threads];
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t tile = blockIdx.x;
@@ -533,6 +539,16 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 incl += t;
         }
         my_off = incl - cnt;
+#if B200_SCAN7_FILL_ALL
+        {   // exclusive survivor offset of every pair of words: all warps fill the candidate list
+            int o = my_off;
+#pragma unroll
+            for (int h2 = 0; h2 < 4; h2++) {
+                s_pair_off[4 * lane + h2] = (uint16_t)o;
+                o += __popc(wv[2 * h2]) + __popc(wv[2 * h2 + 1]);
+            }
+        }
+#endif
         if (lane == 31) {
             const uint32_t total = (uint32_t)incl;
             uint32_t base = 0, ok = 1;
@@ -560,6 +576,23 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     const int C = (int)s_count;
     const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
     for (int win = 0; win < C; win += k7CandCap) {
+#if B200_SCAN7_FILL_ALL
+        {
+            int off = s_pair_off[tid];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int wi = 2 * tid + h;
+                uint32_t wv2 = (wi < P.nw) ? surv[wi] : 0u;
+                while (wv2) {
+                    const int bit = __ffs(wv2) - 1;
+                    wv2 &= wv2 - 1;
+                    if (off >= win && off < win + k7CandCap)
+                        cand[off - win] = (uint16_t)(wi * 32 + bit);
+                    off++;
+                }
+            }
+        }
+#else
         if (warp == 0) {
             int off = my_off;
 #pragma unroll
@@ -574,6 +607,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 }
             }
         }
+#endif
         __syncthreads();
         const int Cw = min(k7CandCap, C - win);
         uint32_t *rec_w = p.rec + 6ull * (s_base + (uint32_t)win);
