@@ -1,0 +1,148 @@
+// dump1090_rs_b200/host/dump1090_b200.cpp -- the reference binary's receive loop
+// (dump1090_rs/src/main.rs:149-213) over libb200adsb, with the SoapySDR front end (out of scope)
+// replaced by a sample source that delivers the same thing stream.read does: up to `mtu`
+// Complex<i16> samples per read, memory order (re, im) = SoapySDR CS16 [I, Q] (main.rs:143,161).
+//
+//   loop { accept one client;  read <= mtu samples;  to_mag + demodulate2400 (fused on the GPU);
+//          "*{hex};\n" per frame -> stdout unless --quiet, and to every TCP client;
+//          clients that reset their connection are dropped }
+//
+// Sources:  --file capture.iq   the reference's capture format (utils.rs:8-40: im, re pairs)
+//           --raw path | -      raw interleaved CS16 (re, im), e.g. a pipe from an SDR tool
+// --batch K collects K reads into one b200adsb_demod_iq_batch call (identical frames, in order).
+// Exits 0 at end of input (the reference exits 1 on an SDR time-out, main.rs:203-209).
+//   g++ -std=c++17 -O2 -o dump1090_b200 dump1090_b200.cpp -L.. -lb200adsb -Wl,-rpath,'$ORIGIN/..'
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "avr_server.hpp"
+#include "dump1090_rs.hpp"
+
+using namespace dump1090_rs;
+
+struct Options {
+    std::string host = "127.0.0.1";     // main.rs:33-40 defaults
+    int port = 30002;
+    bool quiet = false;
+    std::string file, raw;
+    std::size_t mtu = MODES_MAG_BUF_SAMPLES, batch = 1;
+    int wait_clients = 0;               // test aid: do not start before this many clients are connected
+};
+
+static bool parse(int argc, char **argv, Options &o)
+{
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto val = [&](const char *name) -> const char * {
+            if (i + 1 >= argc) {
+                std::fprintf(stderr, "%s needs a value\n", name);
+                std::exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "--host") o.host = val("--host");
+        else if (a == "--port") o.port = std::atoi(val("--port"));
+        else if (a == "--quiet") o.quiet = true;
+        else if (a == "--file") o.file = val("--file");
+        else if (a == "--raw") o.raw = val("--raw");
+        else if (a == "--mtu") o.mtu = (std::size_t)std::atoll(val("--mtu"));
+        else if (a == "--batch") o.batch = (std::size_t)std::atoll(val("--batch"));
+        else if (a == "--wait-clients") o.wait_clients = std::atoi(val("--wait-clients"));
+        else return false;
+    }
+    return (!o.file.empty() || !o.raw.empty()) && o.mtu >= 1 && o.mtu <= MODES_MAG_BUF_SAMPLES && o.batch >= 1;
+}
+
+int main(int argc, char **argv)
+{
+    Options opt;
+    if (!parse(argc, argv, opt)) {
+        std::fprintf(stderr,
+                     "usage: %s (--file capture.iq | --raw path|-) [--host 127.0.0.1] [--port 30002] [--quiet]\n"
+                     "          [--mtu samples<=131072] [--batch reads] [--wait-clients n]\n", argv[0]);
+        return 2;
+    }
+    try {
+        // the sample source
+        std::vector<Complex16> capture;
+        std::size_t cap_pos = 0;
+        std::FILE *rawf = nullptr;
+        if (!opt.file.empty())
+            capture = utils::read_test_data(opt.file);
+        else
+            rawf = opt.raw == "-" ? stdin : std::fopen(opt.raw.c_str(), "rb");
+        if (opt.file.empty() && !rawf)
+            throw std::runtime_error("cannot open " + opt.raw);
+        auto read = [&](Complex16 *dst) -> std::size_t {      // stream.read(&mut [&mut buf], ..) -> len
+            if (rawf)
+                return std::fread(dst, sizeof(Complex16), opt.mtu, rawf);
+            const std::size_t n = std::min(opt.mtu, capture.size() - cap_pos);
+            std::memcpy(dst, capture.data() + cap_pos, n * sizeof(Complex16));
+            cap_pos += n;
+            return n;
+        };
+
+        AvrServer server;
+        server.bind(opt.host, opt.port);
+        std::fprintf(stderr, "[-] listening on %s:%d\n", opt.host.c_str(), server.port());
+        while ((int)server.clients() < opt.wait_clients) {
+            server.accept_one();
+            ::usleep(1000);
+        }
+
+        Context &ctx = Context::global();
+        // pinned staging for `batch` reads (the host entry points accept pageable memory too, only slower)
+        Complex16 *buf = static_cast<Complex16 *>(b200adsb_host_alloc(opt.batch * opt.mtu * sizeof(Complex16)));
+        if (!buf)
+            throw std::runtime_error("pinned allocation failed");
+        std::vector<std::uint32_t> lengths(opt.batch);
+        std::vector<b200adsb_frame> frames(1 << 16);
+        std::size_t total = 0;
+        for (bool eof = false; !eof;) {
+            server.accept_one();                               // main.rs:154-157
+            std::size_t nreads = 0;
+            while (nreads < opt.batch) {
+                const std::size_t len = read(buf + nreads * opt.mtu);
+                if (len == 0) {
+                    eof = true;
+                    break;
+                }
+                lengths[nreads++] = (std::uint32_t)len;
+            }
+            if (nreads == 0)
+                break;
+            std::size_t n = 0;
+            if (nreads == 1)                                   // main.rs:166-167
+                ctx.check(b200adsb_demod_iq(ctx.raw(), reinterpret_cast<const std::int16_t *>(buf), lengths[0],
+                                            frames.data(), frames.size(), &n), "demod_iq");
+            else
+                ctx.check(b200adsb_demod_iq_batch(ctx.raw(), reinterpret_cast<const std::int16_t *>(buf), nreads,
+                                                  opt.mtu, opt.mtu, lengths.data(), frames.data(), frames.size(), &n,
+                                                  nullptr), "demod_iq_batch");
+            if (n == 0)
+                continue;                                      // main.rs:170
+            std::vector<std::string> lines;
+            lines.reserve(n);
+            for (std::size_t i = 0; i < n; i++) {              // main.rs:171-181
+                char line[40];
+                std::size_t len = 0;
+                b200adsb_format_avr(&frames[i], 1, line, sizeof line, &len);
+                lines.emplace_back(line, len);
+                if (!opt.quiet)
+                    std::fwrite(line, 1, len, stdout);
+            }
+            total += n;
+            server.broadcast(lines);                           // main.rs:183-199
+        }
+        std::fflush(stdout);
+        std::fprintf(stderr, "[-] end of input: %zu frames\n", total);
+        b200adsb_host_free(buf);
+        if (rawf && rawf != stdin)
+            std::fclose(rawf);
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "[!] %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

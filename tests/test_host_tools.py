@@ -1,0 +1,91 @@
+"""The host-side pieces around the hot path that SURVEY.md §8(f) ranks next: the AVR/TCP emitter
+(dump1090_rs/src/main.rs:149-200) and the receive loop over a file / pipe source."""
+import os
+import re
+import socket
+import subprocess
+import time
+
+import numpy as np
+import pytest
+
+from conftest import REPO, oracle_stream
+
+HOST = os.path.join(REPO, "dump1090_rs_b200", "host")
+
+
+def _build(name, extra=()):
+    exe = os.path.join(HOST, name)
+    src = exe + ".cpp"
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(
+            os.path.getmtime(os.path.join(HOST, f)) for f in os.listdir(HOST) if f.endswith((".cpp", ".hpp"))):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, src, *extra])
+    return exe
+
+
+def test_avr_server_semantics():
+    """AvrServer alone (no CUDA): non-blocking accept, complete lines to every client in order, a
+    client that resets its connection is dropped (main.rs:154-157,183-199)."""
+    exe = _build("avr_server_test")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    assert "avr_server_test ok" in out.stdout
+
+
+def _start_receiver(args):
+    exe = _build("dump1090_b200", ["-L" + os.path.join(REPO, "dump1090_rs_b200"), "-lb200adsb", "-Wl,-rpath,$ORIGIN/.."])
+    p = subprocess.Popen([exe, "--port", "0", "--wait-clients", "1", *args], stdin=subprocess.PIPE,
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    line = p.stderr.readline().decode()
+    m = re.search(r"listening on [\d.]+:(\d+)", line)
+    assert m, line
+    s = socket.create_connection(("127.0.0.1", int(m.group(1))), timeout=30)
+    return p, s
+
+
+def _drain(sock, p):
+    sock.settimeout(60)
+    data = b""
+    while True:
+        chunk = sock.recv(65536)
+        if not chunk:
+            break
+        data += chunk
+    sock.close()
+    p.wait(timeout=60)
+    return data.decode().split()
+
+
+@pytest.mark.gpu
+def test_receiver_loop_on_capture_file(tmp_path, captures, golden_frames):
+    """dump1090_b200 --file: the reference binary's loop on a capture in the reference's on-disk
+    format; the TCP client and stdout both get the golden AVR lines of tests/test.rs."""
+    from dump1090_rs_b200 import utils
+    name = "test_1641427457780"
+    path = utils.save_test_data(captures[name], str(tmp_path / (name + ".iq")))
+    p, s = _start_receiver(["--file", path])
+    p.stdin.close()
+    got = _drain(s, p)
+    want = ["*" + g["hex"] + ";" for g in golden_frames[name]]
+    assert got == want
+    assert p.stdout.read().decode().split() == want
+    assert p.returncode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", [1, 3])
+def test_receiver_loop_on_raw_pipe(batch, captures, oracle_mod):
+    """dump1090_b200 --raw -: raw CS16 (re, im) from a pipe in reads of 50,000 samples (ragged last
+    read), alone or three reads per call: the lines are the oracle's for the same sequence of reads."""
+    mtu = 50000
+    iq = np.concatenate([captures[k] for k in sorted(captures)])          # 3 x 131072 samples
+    reads = [iq[i:i + mtu] for i in range(0, len(iq), mtu)]
+    ref, _ = oracle_stream(oracle_mod, reads)
+    p, s = _start_receiver(["--raw", "-", "--mtu", str(mtu), "--batch", str(batch), "--quiet"])
+    p.stdin.write(np.ascontiguousarray(iq).tobytes())
+    p.stdin.close()
+    got = _drain(s, p)
+    assert got == ["*" + f["msg"].hex() + ";" for f in ref]
+    assert len(got) > 0
+    assert p.stdout.read() == b""                                         # --quiet
+    assert p.returncode == 0
