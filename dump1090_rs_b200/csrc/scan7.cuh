@@ -306,13 +306,16 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     const int WP = P.WP;
     const int nwq = (NG + 1) / 2;                                // plane words that carry data
 
+    // nothing here conflicts with what the dense phase stores (different addresses), so no barrier
+    // is needed before it: the survivor bitmap, the pad word read by funnel shifts and, for an odd
+    // number of groups, the unowned upper halfword of each row's last data word
     for (int i = tid; i < P.nw; i += k7Threads)
         surv[i] = 0;
-    for (int i = tid; i < 7 * 12; i += k7Threads) {              // words the dense phase may leave unwritten
-        planes[i * WP + nwq - 1] = 0;
+    for (int i = tid; i < 7 * 12; i += k7Threads) {
         planes[i * WP + nwq] = 0;
+        if (NG & 1)
+            reinterpret_cast<uint16_t *>(planes)[2 * (i * WP) + NG] = 0;
     }
-    __syncthreads();
 
     // ---- P1: dense phase (magnitudes, edges, correlator signs; see the header)
     {
