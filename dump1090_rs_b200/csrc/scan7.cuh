@@ -706,6 +706,8 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 }
             }
         }
+        if (win + k7CandCap >= C)
+            break;                       // last window: nothing left to synchronise with
         __syncthreads();
         if (tid == 0) {
             s_nlong = 0;
