@@ -528,13 +528,18 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
             CK(c, cudaGetLastError());
             c->timing.other_launches++;
         }
+        const CommitArgs ca{c->d_ev_keys, c->d_ev_ord, c->d_ev_used, c->d_new_keys, c->d_counters, c->d_members,
+                            d_async_result, ep.cap};
+        const bool fused_commit = q.n_tiles && !save_tail;   // (the tail is saved before the commit)
         if (q.n_tiles) {
-            // one warp per frame; the frame count is only known on the device, so a fixed grid strides
+            // one warp per frame; the frame count is only known on the device, so a fixed grid strides;
+            // one extra block runs the commit step
             const uint32_t eg = (uint32_t)std::min<size_t>(148 * 8, std::max<size_t>(1, (cap + kEmitWarps - 1) / kEmitWarps));
+            CommitArgs none{};
             if (q.from_mag)
-                emit_frames_kernel<true><<<eg, 32 * kEmitWarps, 0, c->stream>>>(ep, c->d_counters, n_ctas);
+                emit_frames_kernel<true><<<eg + 1, 32 * kEmitWarps, 0, c->stream>>>(ep, c->d_counters, n_ctas, fused_commit ? ca : none);
             else
-                emit_frames_kernel<false><<<eg, 32 * kEmitWarps, 0, c->stream>>>(ep, c->d_counters, n_ctas);
+                emit_frames_kernel<false><<<eg + 1, 32 * kEmitWarps, 0, c->stream>>>(ep, c->d_counters, n_ctas, fused_commit ? ca : none);
             CK(c, cudaGetLastError());
         }
         if (save_tail) {
@@ -543,11 +548,14 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
                                                        c->d_tail[c->tail_cur ^ 1]);
             CK(c, cudaGetLastError());
         }
-        events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
-                                                        c->d_new_keys, c->d_counters, c->d_members,
-                                                        d_async_result, ep.cap);
-        CK(c, cudaGetLastError());
-        c->timing.other_launches += 4;
+        if (!fused_commit) {
+            events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
+                                                            c->d_new_keys, c->d_counters, c->d_members,
+                                                            d_async_result, ep.cap);
+            CK(c, cudaGetLastError());
+            c->timing.other_launches++;
+        }
+        c->timing.other_launches += 3;
     }
     if (d_async_result) {
         // enqueue-only form: the batch outcome stays on the device (written by the commit kernel, which

@@ -1599,14 +1599,42 @@ __global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams 
 // binary search over the per-block prefix (32 tiles per resolve block) and a warp scan of that
 // block's 32 tile counts; output slot = f, i.e. (buffer, j) order as before.
 constexpr int kEmitWarps = 8;
+// The commit step has no data dependency on the emit step (it touches the filter, the event table and
+// other counter words), so it rides along as the last block of this launch instead of a launch of
+// its own.
+struct CommitArgs {
+    uint32_t *ev_keys;
+    unsigned long long *ev_ord;
+    const uint32_t *ev_used, *new_keys;
+    uint32_t *counters, *members, *d_result;
+    uint32_t cap;
+};
+__device__ __forceinline__ void commit_tail(const CommitArgs &a)
+{
+    events_commit_body(a.ev_keys, a.ev_ord, a.ev_used, a.new_keys, a.counters, a.members);
+    if (a.d_result && threadIdx.x == 0) {      // enqueue-only batch outcome, per-batch counters cleared
+        a.d_result[0] = a.counters[C_FRAMES];
+        a.d_result[1] = a.counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF);
+        a.d_result[2] = a.counters[C_CAND];
+        a.d_result[3] = a.counters[C_FRAMES] > a.cap ? 1u : 0u;
+        a.counters[C_POOL] = 0;
+        a.counters[C_FLAGS] = 0;
+        a.counters[C_CAND] = 0;
+    }
+}
 template <bool FROM_MAG>
 __global__ void __launch_bounds__(32 * kEmitWarps) emit_frames_kernel(const EmitParams p, const uint32_t *counters,
-                                                                      const uint32_t n_ctas)
+                                                                      const uint32_t n_ctas, const CommitArgs ca)
 {
     __shared__ uint16_t s_mag[kEmitWarps][288];
+    if (blockIdx.x == gridDim.x - 1) {          // the extra block
+        if (ca.counters)
+            commit_tail(ca);
+        return;
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t total = min(counters[C_FRAMES], p.cap);
-    const uint32_t nwarps = gridDim.x * kEmitWarps;
+    const uint32_t nwarps = (gridDim.x - 1) * kEmitWarps;
     for (uint32_t f = blockIdx.x * kEmitWarps + warp; f < total; f += nwarps) {
         // resolve block whose exclusive prefix is the last one <= f: 32-ary search, one probe per lane
         // (two dependent loads for up to 1024 blocks instead of ten)
