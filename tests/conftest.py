@@ -14,6 +14,14 @@ GOLDEN = os.path.join(REPO, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The tests exercise the built product (libb200adsb.so) and the checker (oracle/): in a fresh
+    # checkout neither exists yet (built artefacts are not in the history), so build them once.
+    # nvcc cross-compiles for sm_100a without a GPU; the package itself never builds on import.
+    so = os.path.join(REPO, "dump1090_rs_b200", "libb200adsb.so")
+    orc = os.path.join(REPO, "oracle", "libdump1090_oracle.so")
+    if not (os.path.exists(so) and os.path.exists(orc)):
+        import __graft_entry__ as g
+        g.build()
 
 
 @pytest.fixture(scope="session")
