@@ -337,32 +337,6 @@ __device__ __forceinline__ uint32_t msg_bits(const uint32_t f[5])
     return v;
 }
 
-// src/mode_s/mod.rs:34-139 as a function of the message only
-__device__ __forceinline__ uint32_t classify_fields(const uint32_t *tabs, const uint32_t f[5])
-{
-    if ((f[0] | f[1] | f[2] | f[3] | f[4]) == 0)
-        return kNoneMarker;                      // all 14 bytes zero -> None (:51-53)
-    const uint32_t df = ((f[0] & 1u) << 4) | ((f[1] & 1u) << 3) | ((f[2] & 1u) << 2) |
-                        ((f[3] & 1u) << 1) | (f[4] & 1u);
-    const uint32_t bit = 1u << df;
-    if (bit & 0x00000031u)                       // DF 0,4,5 (:56-72)
-        return (K_PAR_SHORT << 29) | syn56_fields(tabs, f);
-    if (df == 11) {                              // :73-90
-        const uint32_t syn = syn56_fields(tabs, f);
-        if (syn & 0xffff80u)
-            return 0;
-        return (((syn & 0x7f) ? K_DF11_IID : K_DF11_IID0) << 29) | msg_bits<8, 24>(f);
-    }
-    if (bit & 0x00060000u) {                     // DF 17,18 (:91-109)
-        if (syn112_fields(tabs, f) != 0)
-            return 0;
-        return ((df == 17 ? K_DF17 : K_DF18) << 29) | msg_bits<8, 24>(f);
-    }
-    if (bit & 0xFF310000u)                       // DF 16,20,21,24..31 (:110-134)
-        return (K_PAR_LONG << 29) | syn112_fields(tabs, f);
-    return 0;                                    // :135
-}
-
 // byte-wise form for the message-level entry points (crc.rs:263-282 verbatim in spirit)
 __device__ __forceinline__ uint32_t crc_bytes(const uint32_t *tab256, const uint8_t *m, int nbytes)
 {
@@ -471,18 +445,6 @@ __device__ __forceinline__ unsigned long long event_first(const uint32_t *ev_key
         h = (h + 1) & mask;
     }
     return kNever;
-}
-
-// ------------------------------------------------------------------ preamble templates
-// plane[rho][w] bit b  <->  tile mag index 12*(32w+b)+rho.  term(s) returns, for the 32
-// positions of item (rho, w), the plane bit of index position+s.
-__device__ __forceinline__ uint32_t plane_term(const uint32_t *plane, int WP, int rho, int w, int s)
-{
-    int r2 = rho + s;
-    const int c = r2 >= 12;
-    r2 -= 12 * c;
-    const uint32_t *p = plane + r2 * WP + w;
-    return __funnelshift_r(p[0], p[1], c);
 }
 
 // ================================================================== scan kernel
@@ -1283,17 +1245,6 @@ struct ResolveParams {
     unsigned long long ord_first, ord_stride;
 };
 
-__device__ __forceinline__ bool is_member(const ResolveParams &p, uint32_t key, unsigned long long ord)
-{
-    if (key == 0u)
-        return true;                         // icao_filter_test(0) (icao_filter.rs:71,78)
-    if (!bloom_hit(p.bloom, key))
-        return false;
-    if (members_has(p.members, key))
-        return true;
-    return event_first(p.ev_keys, p.ev_ord, p.ev_mask, key) < ord;
-}
-
 // one warp per tile, 32 tiles per block; lanes stride over the tile's records
 constexpr int kResolveThreads = 1024;
 __device__ __forceinline__ void resolve_body(const ResolveParams &p, const uint32_t blk)
@@ -1586,12 +1537,6 @@ __device__ __forceinline__ void emit_body(const EmitParams &p, const uint32_t bl
             out_idx++;
         }
     }
-}
-
-template <bool FROM_MAG>
-__global__ void __launch_bounds__(kResolveThreads) emit_kernel(const EmitParams p)
-{
-    emit_body<FROM_MAG>(p, blockIdx.x);
 }
 
 // Large batches: one warp per FRAME (grid-stride over the batch's frames), so that tiles holding many
