@@ -61,9 +61,9 @@ class B200AdsbError(RuntimeError):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/b200adsb.cu for sm_100a into the in-tree shared library."""
-    srcs = [os.path.join(CSRC, f) for f in ("b200adsb.cu", "kernels.cuh")]
+    import glob
     hdr = os.path.join(_REPO, "include", "b200adsb.h")
-    deps = srcs + [hdr]
+    deps = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh"))) + [hdr]
     stale = (not os.path.exists(SO_PATH)) or any(
         os.path.getmtime(p) > os.path.getmtime(SO_PATH) for p in deps if os.path.exists(p))
     if force or stale:
@@ -121,6 +121,11 @@ _PROTOS = {
     "b200adsb_modes_checksum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
     "b200adsb_score_modes_messages": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "b200adsb_format_avr": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "b200adsb_modes_checksum_one": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]),
+    "b200adsb_score_modes_message": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "b200adsb_getbits": (C.c_uint32, [C.c_void_p, C.c_size_t, C.c_size_t]),
+    "b200adsb_async_acknowledge": (C.c_int, [C.c_void_p]),
+    "b200adsb_debug_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200adsb_debug_crc_tabs": (C.c_int, [C.c_void_p]),
     "b200adsb_debug_mag_sweep": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
 }

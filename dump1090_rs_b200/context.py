@@ -212,6 +212,34 @@ class Context:
                     "modes_checksum")
         return out
 
+    def modes_checksum_one(self, message: bytes, bits: int) -> int:
+        out = C.c_uint32(0)
+        self._check(self._L.b200adsb_modes_checksum_one(self._h, message, len(message), bits, C.byref(out)),
+                    "modes_checksum_one")
+        return int(out.value)
+
+    def score_modes_message(self, msg: bytes):
+        from .demod_2400 import MsgLen
+        ln, sc = C.c_int(0), C.c_int(0)
+        self._check(self._L.b200adsb_score_modes_message(self._h, msg, len(msg), C.byref(ln), C.byref(sc)),
+                    "score_modes_message")
+        if ln.value == 0:
+            return None
+        return (MsgLen.Long if ln.value == 14 else MsgLen.Short, int(sc.value))
+
+    def debug_records(self, cap: int = 1 << 18):
+        """Stage-1 records of the pending batch (between scan_batch_dev and resolve_batch_dev):
+        [(buffer, j, [w4..w8])] in (buffer, j) order."""
+        bufs = np.zeros(cap, dtype=np.uint32)
+        rec = np.zeros((cap, 6), dtype=np.uint32)
+        n = C.c_size_t(0)
+        self._check(self._L.b200adsb_debug_records(self._h, bufs.ctypes.data, rec.ctypes.data, cap, C.byref(n)),
+                    "debug_records")
+        return [(int(bufs[i]), int(rec[i, 0]), [int(x) for x in rec[i, 1:]]) for i in range(n.value)]
+
+    def async_acknowledge(self):
+        self._check(self._L.b200adsb_async_acknowledge(self._h), "async_acknowledge")
+
     def score_modes_messages(self, msgs):
         m = np.ascontiguousarray(msgs, dtype=np.uint8).reshape(-1, 14)
         lens = np.zeros(m.shape[0], dtype=np.uint8)

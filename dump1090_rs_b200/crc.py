@@ -5,11 +5,8 @@ from .context import default_context
 
 
 def modes_checksum(message: bytes, bits: int, ctx=None) -> int:   # src/crc.rs:263-282
-    n = bits // 8
-    assert n >= 3                                                  # crc.rs:267
-    m = np.zeros(14, dtype=np.uint8)
-    m[:n] = np.frombuffer(bytes(message[:n]), dtype=np.uint8)
-    return int((ctx or default_context()).modes_checksum(m, bits)[0])
+    assert bits % 8 == 0 and bits // 8 >= 3 and len(message) >= bits // 8   # crc.rs:264-267
+    return (ctx or default_context()).modes_checksum_one(bytes(message), bits)
 
 
 def modes_checksum_batch(msgs, bits: int, ctx=None) -> np.ndarray:

@@ -47,8 +47,8 @@ struct b200adsb_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     bool own_stream = false;
     int tile_opt = 0, pool_shift = 5, profile = 0, h2d_chunk = 64, carry = 0;
-    uint32_t *d_tail[2] = {nullptr, nullptr};   // carry mode: last 326 IQ samples of the stream (double buffered)
-    int tail_cur = 0;
+    uint32_t *d_tails = nullptr;   // carry mode: last 326 IQ samples of the stream, double buffered
+                                   // (2 x kTailWords; counters[C_TAILCUR] selects the current one)
 
     uint32_t *d_counters = nullptr, *h_counters = nullptr;
     uint32_t *d_members = nullptr;
@@ -57,7 +57,6 @@ struct b200adsb_ctx {
     uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr, *d_lut = nullptr;
     uint32_t h_lut[kLutWords];
     int lut_T = 0, lut_WP = 0;
-    int scan_ver = 7;   // stage-1 kernel generation (B200ADSB_SCAN=6 selects the previous one for A/B runs)
     bool counters_clean = false;     // C_POOL/C_FLAGS/C_CAND already zero (cleared by the last commit kernel)
     uint32_t *d_scalar = nullptr;
 
@@ -206,18 +205,16 @@ int pick_tile(const b200adsb_ctx *c, size_t n_buffers, size_t spb)
 {
     if (c->tile_opt)
         return c->tile_opt;
-    // tile sizes whose halo-extended length is a whole number of 384-sample blocks;
-    // the largest that still gives every SM a few tiles
-    static const int kTiles6[] = {kDefaultTile, 3544, 2008, 856, 472};
-    static const int kTiles7[] = {kDefaultTile, 3544, 1624, 1624, 1624};   // v7: whole warps of 10 groups x 192 samples
-    const int *kTiles = c->scan_ver >= 7 ? kTiles7 : kTiles6;
-    for (int ti = 0; ti < 5; ti++) {
+    // tile sizes whose halo-extended length is a whole number of warp passes (10 groups of 192
+    // samples); the largest that still gives every SM a few tiles
+    static const int kTiles[] = {kDefaultTile, 3544, 1624};   // whole warps of 10 groups x 192 samples
+    for (int ti = 0; ti < 3; ti++) {
         const int t = kTiles[ti];
         const size_t tiles = n_buffers * ((spb + t - 1) / t);
         if (tiles >= 592)
             return t;
     }
-    return kTiles[4];
+    return kTiles[2];
 }
 
 void prof_begin(b200adsb_ctx *c, std::vector<EventPair> &v)
@@ -268,33 +265,8 @@ int read_counters(b200adsb_ctx *c)
 int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
 {
     const Pending &q = c->cur;
-    ScanParams p{};
-    if (q.from_mag)
-        p.in = reinterpret_cast<const uint16_t *>(q.in) + (size_t)b0 * q.stride;
-    else
-        p.in = reinterpret_cast<const int16_t *>(q.in) + 2 * (size_t)b0 * q.stride;
-    p.lengths = q.lengths ? q.lengths + b0 : nullptr;
-    p.n_buffers = nb;
-    p.spb = q.spb;
-    p.stride = q.stride;
-    p.T = q.T;
-    p.tiles_per_buffer = q.tpb;
-    p.vec_ok = (!q.from_mag && ((uintptr_t)q.in % 16 == 0) && (q.stride % 4 == 0)) ? 1 : 0;
-    p.rec = c->d_rec;
-    p.pool_cap = (uint32_t)std::min<size_t>(c->pool_cap, 0xffffffffu);
-    p.tile_dir = c->d_tile_dir + (size_t)b0 * q.tpb;
-    p.counters = c->d_counters;
-    p.ev_keys = c->d_ev_keys;
-    p.ev_ord = c->d_ev_ord;
-    p.ev_used = c->d_ev_used;
-    p.ev_mask = kEvSlots - 1;
-    p.ord_first = q.ord_first + (unsigned long long)b0 * q.ord_stride;
-    p.ord_stride = q.ord_stride;
-    p.crc_tabs = c->d_crc_tabs;
-    ScanSmem L(q.T);
     Scan7Smem L7(q.T);
-    const int WPsel = c->scan_ver >= 7 ? L7.WP : L.WP;
-    if (c->lut_T != q.T || c->lut_WP != WPsel) {
+    if (c->lut_T != q.T || c->lut_WP != L7.WP) {
         // field r of try-phase 4+tt of a candidate whose A = j+19 has A % 12 == ra starts at
         // 1/5-sample position 5*(A+e5)+z: word offset of its plane/residue stream in
         // plane[phi][rho][WP], and whether the stream index q = A/12 advances by one
@@ -303,65 +275,57 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
             const int e5 = (tt >= 1) ? 1 : 0, phi0 = (tt >= 1) ? tt - 1 : 4;
             const int z = phi0 + 12 * r, zd = z / 5, phi = z - 5 * zd;
             const int rr = ra + e5 + zd, wrap = rr >= 12 ? 1 : 0;
-            c->h_lut[i] = (uint32_t)((phi * 12 + rr - 12 * wrap) * WPsel) | ((uint32_t)wrap << 16);
+            c->h_lut[i] = (uint32_t)((phi * 12 + rr - 12 * wrap) * L7.WP) | ((uint32_t)wrap << 16);
         }
         CK(c, cudaStreamSynchronize(c->stream));   // a previous launch may still read the table
         CK(c, cudaMemcpyAsync(c->d_lut, c->h_lut, sizeof c->h_lut, cudaMemcpyHostToDevice, c->stream));
         c->lut_T = q.T;
-        c->lut_WP = WPsel;
+        c->lut_WP = L7.WP;
     }
+    Scan7Params P7{};
+    ScanParams &p = P7.s;
+    p.in = q.in;               // the kernel indexes buffers and tiles of the whole batch (carry mode reaches
+    p.lengths = q.lengths;     // back into buffer b0-1 of the batch, not into the previous batch)
+    p.b0 = b0;
+    p.n_buffers = nb;
+    p.spb = q.spb;
+    p.stride = q.stride;
+    p.T = q.T;
+    p.tiles_per_buffer = q.tpb;
+    p.vec_ok = (!q.from_mag && ((uintptr_t)q.in % 16 == 0) && (q.stride % 4 == 0)) ? 1 : 0;
+    p.rec = c->d_rec;
+    p.pool_cap = (uint32_t)std::min<size_t>(c->pool_cap, 0xffffffffu);
+    p.tile_dir = c->d_tile_dir;
+    p.counters = c->d_counters;
+    p.ev_keys = c->d_ev_keys;
+    p.ev_ord = c->d_ev_ord;
+    p.ev_used = c->d_ev_used;
+    p.ev_mask = kEvSlots - 1;
+    p.ord_first = q.ord_first;
+    p.ord_stride = q.ord_stride;
+    p.crc_tabs = c->d_crc_tabs;
     p.lut = c->d_lut;
     p.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
-    p.tail = c->d_tail[c->tail_cur];
-    p.off_dd = (uint32_t)L.off_dd;
-    p.off_planes = (uint32_t)L.off_planes;
-    p.off_edges = (uint32_t)L.off_edges;
-    p.edge_bytes = (uint32_t)L.edge_bytes;
-    p.off_surv = (uint32_t)L.off_surv;
-    p.off_queue = (uint32_t)L.off_queue;
-    p.off_cand = (uint32_t)L.off_cand;
-    p.WP = L.WP;
-    p.nw = L.nw;
-    if (const char *ex = getenv("B200ADSB_DEBUG_EXTRA_SMEM"))   // occupancy experiments only
-        L.bytes += (size_t)atoi(ex);
+    p.tails = c->d_tails;
+    P7.off_planes = (uint32_t)L7.off_planes;
+    P7.off_surv = (uint32_t)L7.off_surv;
+    P7.off_masks = (uint32_t)L7.off_masks;
+    P7.off_list = (uint32_t)L7.off_list;
+    P7.off_cand = (uint32_t)L7.off_cand;
+    P7.NG = L7.NG;
+    P7.WP = L7.WP;
+    P7.nw = L7.nw;
+    P7.list_cap = L7.list_cap;
+    P7.Wrow = (L7.NG + 1) / 2;
+    P7.inv_Wrow = (65536 + P7.Wrow - 1) / P7.Wrow;
     const uint32_t grid = nb * (uint32_t)q.tpb;
     if (grid == 0)
         return B200ADSB_OK;
     prof_begin(c, c->scan_events);
-    if (c->scan_ver >= 7) {
-        Scan7Params P7;
-        P7.s = p;
-        P7.off_planes = (uint32_t)L7.off_planes;
-        P7.off_surv = (uint32_t)L7.off_surv;
-        P7.off_masks = (uint32_t)L7.off_masks;
-        P7.off_list = (uint32_t)L7.off_list;
-        P7.off_cand = (uint32_t)L7.off_cand;
-        P7.NG = L7.NG;
-        P7.WP = L7.WP;
-        P7.nw = L7.nw;
-        P7.Wrow = (L7.NG + 1) / 2;
-        P7.inv_Wrow = (65536 + P7.Wrow - 1) / P7.Wrow;
-        size_t bytes7 = L7.bytes;
-        if (const char *ex = getenv("B200ADSB_DEBUG_EXTRA_SMEM"))
-            bytes7 += (size_t)atoi(ex);
-        if (q.from_mag) {
-            CK(c, cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes7));
-            CK(c, cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            scan7_kernel<true><<<grid, k7Threads, bytes7, c->stream>>>(P7);
-        } else {
-            CK(c, cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes7));
-            CK(c, cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            scan7_kernel<false><<<grid, k7Threads, bytes7, c->stream>>>(P7);
-        }
-    } else if (q.from_mag) {
-        CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-        CK(c, cudaFuncSetAttribute(scan_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        scan_kernel<true><<<grid, kThreads, L.bytes, c->stream>>>(p);
-    } else {
-        CK(c, cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.bytes));
-        CK(c, cudaFuncSetAttribute(scan_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        scan_kernel<false><<<grid, kThreads, L.bytes, c->stream>>>(p);
-    }
+    if (q.from_mag)
+        scan7_kernel<true><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
+    else
+        scan7_kernel<false><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
     prof_end(c, c->scan_events);
     CK(c, cudaGetLastError());
     c->timing.scan_launches++;
@@ -369,8 +333,12 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     return B200ADSB_OK;
 }
 
-int reset_scan_counters(b200adsb_ctx *c)
+// per-batch counters to zero before stage 1.  A synchronous call also acknowledges a failed
+// enqueue-only batch (it is the documented way to redo one): the sticky flag is cleared.
+int reset_scan_counters(b200adsb_ctx *c, bool enqueue_only = false)
 {
+    if (!enqueue_only)
+        CK(c, cudaMemsetAsync(c->d_counters + C_STICKY, 0, 4, c->stream));
     if (c->counters_clean) {   // the previous (enqueue-only) batch cleared them on the device
         c->counters_clean = false;
         return B200ADSB_OK;
@@ -383,8 +351,10 @@ int reset_scan_counters(b200adsb_ctx *c)
 
 int clear_events(b200adsb_ctx *c)
 {
-    events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
-                                                    c->d_new_keys, c->d_counters, c->d_members);
+    // (C_FLAGS still holds the overflow that brought us here: nothing is admitted)
+    const CommitArgs ca{c->d_ev_keys, c->d_ev_ord, c->d_ev_used, c->d_new_keys, c->d_counters, c->d_members,
+                        nullptr, 0u, 0};
+    events_commit_kernel<<<1, 1024, 0, c->stream>>>(ca);
     CK(c, cudaGetLastError());
     c->timing.other_launches++;
     return B200ADSB_OK;
@@ -451,9 +421,26 @@ int scan_run_all(b200adsb_ctx *c)
     return B200ADSB_ERR_NOMEM;
 }
 
+// every exit of a call that owns a pending batch ends it (a failed call must not leave the
+// context refusing all later calls with ERR_STATE)
+struct PendingGuard {
+    b200adsb_ctx *c;
+    ~PendingGuard() { c->cur.active = false; }
+};
+
 // stage 2: finalise events, resolve, ordered emit, commit
+int resolve_run_impl(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
+                     uint32_t *d_per_buffer_counts, uint32_t *d_async_result);
 int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
                 uint32_t *d_per_buffer_counts, uint32_t *d_async_result = nullptr)
+{
+    const int rc = resolve_run_impl(c, d_out, cap, n_out, d_per_buffer_counts, d_async_result);
+    if (rc != kRedo)      // kRedo: the caller redoes the scan on the same pending batch
+        c->cur.active = false;
+    return rc;
+}
+int resolve_run_impl(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_out,
+                     uint32_t *d_per_buffer_counts, uint32_t *d_async_result)
 {
     Pending &q = c->cur;
     if (!q.active)
@@ -487,7 +474,8 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     ep.tile_dir = c->d_tile_dir;
     ep.emit_info = c->d_emit_info;
     ep.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
-    ep.tail = c->d_tail[c->tail_cur];
+    ep.tails = c->d_tails;
+    ep.counters = c->d_counters;
     ep.tile_cnt = c->d_tile_emit;
     ep.cta_excl = c->d_cta_sum;
     ep.n_tiles = q.n_tiles;
@@ -500,15 +488,14 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     if (small) {
         // one launch for the whole second stage (the tail is saved first: commit ends the kernel)
         if (save_tail) {
-            save_tail_kernel<<<1, 352, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride, q.lengths,
-                                                       q.spb, q.n_buffers, c->d_tail[c->tail_cur],
-                                                       c->d_tail[c->tail_cur ^ 1]);
+            save_tail_kernel<<<1, kTailWords, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride,
+                                                              q.lengths, q.spb, q.n_buffers, c->d_tails, c->d_counters);
             CK(c, cudaGetLastError());
         }
         if (q.from_mag)
-            resolve_small_kernel<true><<<1, kResolveThreads, 0, c->stream>>>(fa, rp, ep, n_ctas);
+            resolve_small_kernel<true><<<1, kResolveThreads, 0, c->stream>>>(fa, rp, ep, n_ctas, save_tail ? 1 : 0);
         else
-            resolve_small_kernel<false><<<1, kResolveThreads, 0, c->stream>>>(fa, rp, ep, n_ctas);
+            resolve_small_kernel<false><<<1, kResolveThreads, 0, c->stream>>>(fa, rp, ep, n_ctas, save_tail ? 1 : 0);
         CK(c, cudaGetLastError());
         c->timing.other_launches += 1 + (save_tail ? 1 : 0);
     } else {
@@ -529,7 +516,7 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
             c->timing.other_launches++;
         }
         const CommitArgs ca{c->d_ev_keys, c->d_ev_ord, c->d_ev_used, c->d_new_keys, c->d_counters, c->d_members,
-                            d_async_result, ep.cap};
+                            d_async_result, ep.cap, save_tail ? 1 : 0};
         const bool fused_commit = q.n_tiles && !save_tail;   // (the tail is saved before the commit)
         if (q.n_tiles) {
             // one warp per frame; the frame count is only known on the device, so a fixed grid strides;
@@ -543,15 +530,12 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
             CK(c, cudaGetLastError());
         }
         if (save_tail) {
-            save_tail_kernel<<<1, 352, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride, q.lengths,
-                                                       q.spb, q.n_buffers, c->d_tail[c->tail_cur],
-                                                       c->d_tail[c->tail_cur ^ 1]);
+            save_tail_kernel<<<1, kTailWords, 0, c->stream>>>(reinterpret_cast<const uint32_t *>(q.in), q.stride,
+                                                              q.lengths, q.spb, q.n_buffers, c->d_tails, c->d_counters);
             CK(c, cudaGetLastError());
         }
         if (!fused_commit) {
-            events_commit_kernel<<<1, 1024, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used,
-                                                            c->d_new_keys, c->d_counters, c->d_members,
-                                                            d_async_result, ep.cap);
+            events_commit_kernel<<<1, 1024, 0, c->stream>>>(ca);
             CK(c, cudaGetLastError());
             c->timing.other_launches++;
         }
@@ -563,8 +547,6 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
         c->counters_clean = !small;
         prof_end(c, c->other_events);
         q.active = false;
-        if (save_tail)
-            c->tail_cur ^= 1;
         return B200ADSB_OK;
     }
     prof_end(c, c->other_events);
@@ -573,8 +555,6 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
     if (c->h_counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF))
         return kRedo;   // optimistic scan overflowed: nothing was committed, the caller redoes it
     q.active = false;
-    if (save_tail)
-        c->tail_cur ^= 1;
     c->timing.candidates += c->h_counters[C_CAND];
     const size_t n = c->h_counters[C_FRAMES];
     if (n_out)
@@ -588,6 +568,7 @@ int resolve_run(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t *n_ou
 int scan_resolve(b200adsb_ctx *c, bool scanned, b200adsb_frame *d_out, size_t cap, size_t *n_out,
                  uint32_t *d_per_buffer_counts)
 {
+    PendingGuard guard{c};
     int rc;
     if (!scanned) {
         rc = reset_scan_counters(c);
@@ -663,8 +644,13 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
             return fail(B200ADSB_ERR_CUDA); \
     } while (0)
     CKC(cudaSetDevice(device));
-    if (const char *sv = getenv("B200ADSB_SCAN"))
-        c->scan_ver = atoi(sv) == 6 ? 6 : 7;
+    {   // the scan kernel's launch attributes, once: room for the largest tile, all of L1 as shared memory
+        const int max_smem = (int)Scan7Smem(kMaxTile).bytes;
+        CKC(cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CKC(cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        CKC(cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        CKC(cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    }
     if (stream) {
         c->stream = (cudaStream_t)stream;
     } else {
@@ -688,10 +674,8 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     CKC(cudaMalloc((void **)&c->d_crc256, 256 * 4));
     CKC(cudaMalloc((void **)&c->d_lut, kLutWords * 4));
     CKC(cudaMalloc((void **)&c->d_bloom, kBloomWords * 4));
-    for (int i = 0; i < 2; i++) {
-        CKC(cudaMalloc((void **)&c->d_tail[i], 352 * 4));
-        CKC(cudaMemset(c->d_tail[i], 0, 352 * 4));
-    }
+    CKC(cudaMalloc((void **)&c->d_tails, 2 * kTailWords * 4));
+    CKC(cudaMemset(c->d_tails, 0, 2 * kTailWords * 4));
     CKC(cudaMalloc((void **)&c->d_scalar, 64));
     {
         uint32_t t[kTabWords], t256[256];
@@ -733,8 +717,7 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_tile_emit);
     cudaFree(c->d_cta_sum);
     cudaFree(c->d_bloom);
-    cudaFree(c->d_tail[0]);
-    cudaFree(c->d_tail[1]);
+    cudaFree(c->d_tails);
     cudaFree(c->d_stage);
     cudaFree(c->d_frames);
     cudaFree(c->d_counts);
@@ -765,7 +748,7 @@ int b200adsb_ctx_set_option(b200adsb_ctx *c, int option, int64_t value)
     case B200ADSB_OPT_CARRY:
         c->carry = value ? 1 : 0;   // (re)starting continuity: nothing precedes the next buffer
         if (cudaSetDevice(c->device) != cudaSuccess ||
-            cudaMemsetAsync(c->d_tail[c->tail_cur], 0, 352 * 4, c->stream) != cudaSuccess)
+            cudaMemsetAsync(c->d_tails, 0, 2 * kTailWords * 4, c->stream) != cudaSuccess)
             return B200ADSB_ERR_CUDA;
         return B200ADSB_OK;
     case B200ADSB_OPT_H2D_CHUNK:
@@ -869,7 +852,7 @@ int b200adsb_scan_batch_dev_async(b200adsb_ctx *c, const int16_t *d_iq, size_t n
     rc = scan_begin(c, d_iq, false, n_buffers, spb, stride, d_lengths, first_ordinal,
                     ordinal_stride ? ordinal_stride : 1);
     if (rc) return rc;
-    rc = reset_scan_counters(c);
+    rc = reset_scan_counters(c, true);
     if (!rc)
         rc = launch_scan(c, 0, c->cur.n_buffers);
     if (rc)
@@ -990,11 +973,14 @@ int b200adsb_demod_iq_batch_dev_async(b200adsb_ctx *c, const int16_t *d_iq, size
     rc = scan_begin(c, d_iq, false, n_buffers, spb, stride, d_lengths, c->next_ordinal, 1);
     if (rc) return rc;
     c->next_ordinal += n_buffers;
-    rc = reset_scan_counters(c);
+    rc = reset_scan_counters(c, true);
     if (rc) { c->cur.active = false; return rc; }
     rc = launch_scan(c, 0, c->cur.n_buffers);
     if (rc) { c->cur.active = false; return rc; }
-    return resolve_run(c, d_out, cap, nullptr, nullptr, d_result);
+    rc = resolve_run(c, d_out, cap, nullptr, nullptr, d_result);
+    if (rc)
+        c->cur.active = false;
+    return rc;
 }
 
 int b200adsb_demod_iq_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_buffers, size_t spb,
@@ -1052,6 +1038,7 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers
         }
         rc = scan_begin(c, d_iq, false, nb, spb, dstride, d_len, c->next_ordinal, 1);
         if (rc) return rc;
+        PendingGuard guard{c};
         // H2D in chunks on the copy stream, scan of chunk k overlapping the copy of chunk k+1
         const size_t chunk = (size_t)c->h2d_chunk;
         const size_t n_chunks = nb ? (nb + chunk - 1) / chunk : 0;
@@ -1315,6 +1302,69 @@ int b200adsb_score_modes_messages(b200adsb_ctx *c, const uint8_t *msgs, size_t n
     return B200ADSB_OK;
 }
 
+/* single-message forms with the reference's own shapes (crc.rs:263, mode_s/mod.rs:14,34) */
+int b200adsb_modes_checksum_one(b200adsb_ctx *c, const uint8_t *msg, size_t n_bytes, size_t bits, uint32_t *out)
+{
+    // the reference asserts bits % 8 == 0 and bits / 8 <= msg.len() with at least 3 bytes (crc.rs:264-267)
+    if (!c || !msg || !out || (bits != 56 && bits != 112) || n_bytes < bits / 8)
+        return B200ADSB_ERR_BAD_ARG;
+    uint8_t m14[14] = {0};
+    memcpy(m14, msg, std::min<size_t>(n_bytes, 14));
+    return b200adsb_modes_checksum(c, m14, 1, bits, out);
+}
+
+int b200adsb_score_modes_message(b200adsb_ctx *c, const uint8_t *msg, size_t n_bytes, int *msglen, int *score)
+{
+    if (!c || !msg || !msglen || !score)
+        return B200ADSB_ERR_BAD_ARG;
+    *msglen = 0;
+    *score = 0;
+    // mode_s/mod.rs:35-49: None when the slice is shorter than the length its DF announces
+    if (n_bytes < (size_t)B200ADSB_MODES_SHORT_MSG_BYTES)
+        return B200ADSB_OK;
+    const size_t need = (msg[0] & 0x80) ? B200ADSB_MODES_LONG_MSG_BYTES : B200ADSB_MODES_SHORT_MSG_BYTES;
+    if (n_bytes < need)
+        return B200ADSB_OK;
+    // :51 looks at every byte of the slice it was given (the scan always hands over 14)
+    bool any = false;
+    for (size_t k = 0; k < n_bytes; k++)
+        any |= msg[k] != 0;
+    if (!any)
+        return B200ADSB_OK;
+    uint8_t m14[14] = {0};
+    memcpy(m14, msg, std::min<size_t>(n_bytes, 14));
+    uint8_t len = 0;
+    int32_t sc = 0;
+    const int rc = b200adsb_score_modes_messages(c, m14, 1, &len, &sc);
+    if (rc)
+        return rc;
+    *msglen = (int)need;
+    *score = sc;
+    return B200ADSB_OK;
+}
+
+uint32_t b200adsb_getbits(const uint8_t *data, size_t firstbit_1idx, size_t lastbit_1idx)   /* mode_s/mod.rs:14-30 */
+{
+    uint32_t ans = 0;
+    if (!data || firstbit_1idx == 0)
+        return 0;
+    for (size_t bit = firstbit_1idx - 1; bit + 1 <= lastbit_1idx; bit++)
+        ans = (ans << 1) | ((data[bit / 8] >> (7 - bit % 8)) & 1u);
+    return ans;
+}
+
+/* acknowledges a failed enqueue-only batch (d_result[1] != 0): the batches queued after this call
+ * commit again.  Stream ordered; any synchronous demodulation call does the same. */
+int b200adsb_async_acknowledge(b200adsb_ctx *c)
+{
+    if (!c)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    CK(c, cudaMemsetAsync(c->d_counters + C_STICKY, 0, 4, c->stream));
+    return B200ADSB_OK;
+}
+
 /* dump1090_rs/src/main.rs:174-176: one "*{hex};\n" line per frame (the AVR text the
  * reference writes to its TCP clients).  Pure host formatting of frames already demodulated. */
 int b200adsb_format_avr(const b200adsb_frame *frames, size_t n, char *out, size_t cap, size_t *len)
@@ -1364,6 +1414,41 @@ int b200adsb_debug_mag_sweep(b200adsb_ctx *c, uint64_t *mismatches, uint32_t *fi
     CK(c, cudaStreamSynchronize(c->stream));
     *mismatches = m;
     return B200ADSB_OK;
+}
+
+/* test hook: the stage-1 records of the pending batch (valid between b200adsb_scan_batch_dev and
+ * b200adsb_resolve_batch_dev): for every position that passed the preamble gates, in (buffer, j)
+ * order, the batch buffer index and the six record words {j, w[5]} (w[t-4] = kind<<29 | key of
+ * try-phase t) -- the per-stage parity point of SURVEY.md section 7 steps 4-5 (survivor set and
+ * per-(j, t) classification, src/demod_2400.rs:127-146,158-189, src/mode_s/mod.rs:34-139). */
+int b200adsb_debug_records(b200adsb_ctx *c, uint32_t *buffers, uint32_t *rec6, size_t cap, size_t *n_out)
+{
+    if (!c || !n_out || (cap && (!buffers || !rec6)))
+        return B200ADSB_ERR_BAD_ARG;
+    if (!c->cur.active)
+        return B200ADSB_ERR_STATE;
+    int rc = bind(c);
+    if (rc) return rc;
+    const Pending &q = c->cur;
+    rc = read_counters(c);
+    if (rc) return rc;
+    const size_t used = c->h_counters[C_POOL];
+    std::vector<uint2> dir(q.n_tiles);
+    std::vector<uint32_t> pool(6 * std::max<size_t>(used, 1));
+    if (q.n_tiles)
+        CK(c, cudaMemcpy(dir.data(), c->d_tile_dir, q.n_tiles * sizeof(uint2), cudaMemcpyDeviceToHost));
+    if (used)
+        CK(c, cudaMemcpy(pool.data(), c->d_rec, used * 24, cudaMemcpyDeviceToHost));
+    size_t n = 0;
+    for (uint32_t t = 0; t < q.n_tiles; t++)
+        for (uint32_t i = 0; i < dir[t].y; i++, n++) {
+            if (n >= cap)
+                continue;
+            buffers[n] = t / (uint32_t)std::max(q.tpb, 1);
+            memcpy(rec6 + 6 * n, pool.data() + 6 * ((size_t)dir[t].x + i), 24);
+        }
+    *n_out = n;
+    return n > cap ? B200ADSB_ERR_CAPACITY : B200ADSB_OK;
 }
 
 /* test hook (pure host): the CRC-24 field tables the scan kernel uses, so that CPU

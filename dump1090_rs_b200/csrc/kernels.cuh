@@ -2,25 +2,20 @@
 //
 // The reference scans one sample at a time on one CPU thread
 // (src/demod_2400.rs:115-212).  Here the same arithmetic is re-organised for a GPU.
-// This file holds what both generations of the stage-1 kernel share (exact fast magnitude,
-// CRC-24 by fields, classification, event table, gates), the previous generation itself
-// (scan_kernel, "v6", selectable with B200ADSB_SCAN=6 for A/B runs; the current one is
-// scan7_kernel in scan7.cuh), stage 2 and the API-parity kernels.
+// This file holds what the stage-1 kernel (scan7_kernel, scan7.cuh) shares with the rest
+// (exact fast magnitude, CRC-24 by fields, classification, event table, gates), stage 2
+// and the API-parity kernels.
 //
-//   scan_kernel (one thread block per tile of T output positions)
-//     P1  IQ -> u16 magnitude, edge bits and first differences into shared memory
-//                                                          (src/utils.rs:43-58)
-//     P2  every sample's five PPM correlator signs as bit planes de-interleaved modulo 12
-//         samples (one Mode-S bit period at 2.4 Msps is 12/5 samples, so message bit n of
-//         try-phase t lives at 1/5-sample position P = 5(j+19)+t+12n: sample P/5,
-//         correlator P%5)                                  (src/demod_2400.rs:62-83,158-182)
-//     P3  the five preamble templates evaluated 32 positions at a time as AND/shift
-//         of the edge bitmaps, then SNR + quiet-zone gates on the matches
-//                                                          (src/demod_2400.rs:127-146,215-321)
-//     P4  per surviving position and try-phase: five 23-bit field extracts from
-//         the planes, DF, CRC-24 syndrome by table (GF(2)-linear), stateless
-//         classification -> one 24-byte record; ICAO add-events by atomicMin
-//                                                          (src/mode_s/mod.rs:34-139, src/crc.rs:263-282)
+//   stage 1 (scan7.cuh, one thread block per tile of T output positions)
+//     IQ -> u16 magnitude (src/utils.rs:43-58); edge bits and the five PPM correlator signs of
+//     every sample as bit planes de-interleaved modulo 12 samples (one Mode-S bit period at
+//     2.4 Msps is 12/5 samples, so message bit n of try-phase t lives at 1/5-sample position
+//     P = 5(j+19)+t+12n: sample P/5, correlator P%5)      (src/demod_2400.rs:62-83,158-182);
+//     the five preamble templates as AND/shift of the edge planes, SNR + quiet-zone gates
+//     (src/demod_2400.rs:127-146,215-321); per surviving position and try-phase five 23-bit
+//     field extracts, DF, CRC-24 syndrome by table (GF(2)-linear), stateless classification
+//     -> one 24-byte record; ICAO add-events by atomicMin
+//                                          (src/mode_s/mod.rs:34-139, src/crc.rs:263-282)
 //   finalize / resolve / emit / commit kernels
 //         the sequential ICAO filter (src/icao_filter.rs) evaluated order-free:
 //         member(a) at ordinal o  <=>  a == 0 || a in filter before the batch ||
@@ -32,14 +27,6 @@
 
 #include "../../include/b200adsb.h"
 
-// build-time experiment knobs (scripts/ab.sh compiles variants with -D...)
-#ifndef B200_SCAN_MIN_BLOCKS
-#define B200_SCAN_MIN_BLOCKS 5
-#endif
-#ifndef B200_AGG_ATOMICS
-#define B200_AGG_ATOMICS 1
-#endif
-
 namespace b200 {
 
 constexpr int kTrailing = B200ADSB_TRAILING_SAMPLES;          // lib.rs:24
@@ -47,19 +34,9 @@ constexpr int kMaxSamples = B200ADSB_MODES_MAG_BUF_SAMPLES;    // lib.rs:22
 constexpr int kMagLen = B200ADSB_MAG_DATA_LEN;
 constexpr int kHaloFront = 2;    // tile mag index 0 <-> data index tile_start-2 (16 B aligned IQ loads)
 constexpr int kHaloTot = 296;    // mags needed per tile = T + 296 (max tap j+289, +2 front, padded to 8)
-constexpr int kStep = 384;       // 12 residues x 32 lanes: samples per warp step
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 248;      // new pair-slots per warp iteration of P1 (8 per lane, lane 31 overlaps)
-constexpr int kHalf = 192;       // half block: 12 residues x 16 lanes-steps
-constexpr int kQuarter = 96;     // P2 task = 8 samples at stride 12 of one residue class
-constexpr int kQuarterPad = 108; // 96 pair-slots + 12 mirrored from the next quarter block (bank skew 12)
-constexpr int kQueueCap = 256;   // template matches per template case awaiting the gates (overflow: in place)
-constexpr int kCandCap = 176;    // survivors decoded per window
-constexpr int kFieldItems = 5 * kCandCap;   // (survivor, try_phase) items whose fields are staged
 constexpr int kLutWords = 12 * 25;          // field-extraction table: (residue of j+19, try_phase, field)
 constexpr int kMaxTile = 8184;   // tile mag indices (< T+2) fit 13 bits; surv words <= 256
-constexpr int kDefaultTile = 7384;   // 20 blocks of 384: 16 P1 chunks (2 per warp), 240 P2 tasks, 231 P3 words
+constexpr int kDefaultTile = 7384;   // 40 x 192 - 296: the halo-extended tile is 40 groups of 192 samples
 constexpr int kTabWords = 256 + 256 + 64 + 256 + 8;   // CRC-24 field tables (see build_crc_tabs)
 constexpr int kTab56 = 576;
 
@@ -72,23 +49,32 @@ constexpr uint32_t kNoneMarker = 1;  // kind NONE, key 1: score_modes_message re
 
 // counters block (device, u32)
 enum { C_POOL = 0, C_FLAGS = 1, C_EV_USED = 2, C_FRAMES = 3, C_CAND = 4, C_MEMBERS = 5,
-       C_ADMIT = 6, C_NEWCNT = 7, C_TICKET = 8, C_WORDS = 16 };
-enum : uint32_t { F_POOL_OVF = 1, F_EV_OVF = 2, F_FILTER_FULL = 4 };
+       C_ADMIT = 6, C_NEWCNT = 7, C_TICKET = 8,
+       C_STICKY = 9,    // enqueue-only batches: an earlier queued batch failed and the host has not acknowledged it
+       C_TAILCUR = 10,  // carry mode: which of the two stream tails is current (flipped by a committed batch)
+       C_WORDS = 16 };
+// F_POOL_OVF .. F_REMOTE_BAD make a batch "bad": it is not committed to the filter (and, in carry mode,
+// does not advance the stream tail).  F_SKIPPED / F_REMOTE_BAD also appear in d_result[1] of the
+// enqueue-only calls (include/b200adsb.h).
+enum : uint32_t { F_POOL_OVF = 1, F_EV_OVF = 2, F_FILTER_FULL = 4, F_SKIPPED = 8, F_REMOTE_BAD = 16 };
+constexpr uint32_t kBadMask = F_POOL_OVF | F_EV_OVF | F_REMOTE_BAD;
+constexpr int kTailWords = 352;   // kTrailing rounded up
 
 constexpr uint32_t kMemberSlots = 8192;   // open addressing, >= 2 x 4096 keys
 constexpr unsigned long long kNever = ~0ull;
 
 struct ScanParams {
-    const void *in;            // int16 (re,im) pairs, or u16 MagnitudeBuffer.data
-    const uint32_t *lengths;   // nullable per-buffer sample counts
-    uint32_t n_buffers;
+    const void *in;            // int16 (re,im) pairs, or u16 MagnitudeBuffer.data: buffer 0 of the BATCH
+    const uint32_t *lengths;   // nullable per-buffer sample counts (indexed by batch buffer)
+    uint32_t b0;               // first batch buffer of this launch (the host API scans per H2D chunk)
+    uint32_t n_buffers;        // buffers of this launch
     uint32_t spb;              // samples per buffer (length when lengths == NULL)
     unsigned long long stride; // IQ: samples between buffers; MAG: u16 elements
     int T, tiles_per_buffer;
     int vec_ok;                // 16-byte aligned base and stride % 4 == 0
     uint32_t *rec;             // pool of 6-word records {j, w[5]}
     uint32_t pool_cap;
-    uint2 *tile_dir;           // per tile: (pool base, count)
+    uint2 *tile_dir;           // per tile of the batch: (pool base, count)
     uint32_t *counters;
     uint32_t *ev_keys;
     unsigned long long *ev_ord;
@@ -97,53 +83,10 @@ struct ScanParams {
     unsigned long long ord_first, ord_stride;
     const uint32_t *crc_tabs;  // CRC-24 field tables (global memory, L1 resident)
     const uint32_t *lut;       // [12][5][5] field extraction table for this tile size
-    // shared memory layout of ScanSmem(T), computed once on the host
-    uint32_t off_dd, off_planes, off_edges, edge_bytes, off_surv, off_queue, off_cand;
-    int WP, nw;
     // opt-in stream continuity (B200ADSB_OPT_CARRY): the 326 leading MagnitudeBuffer slots of a
     // buffer hold the previous buffer's last samples instead of zeros
     int carry;
-    const uint32_t *tail;      // last 326 IQ samples of the stream before this batch
-};
-
-__host__ __device__ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
-
-// shared memory plan of the scan kernel for tile size T.
-// The halo-extended tile is H blocks of 384 samples = 2H half blocks of 192; the first H half
-// blocks form stream A, the last H stream B, and everything downstream of the magnitude works
-// on (A, B) sample pairs in the packed f32x2 pipe.
-struct ScanSmem {
-    int steps, MP, MPc, WP, nw, dd_words, edge_bytes;
-    size_t off_dd, off_planes, off_edges, off_surv, off_tabs, off_queue, off_cand, off_lut, bytes;
-    __host__ __device__ explicit ScanSmem(int T)
-    {
-        steps = (T + kHaloTot + kStep - 1) / kStep;   // H: 384-sample blocks
-        MP = steps * kStep;
-        MPc = MP + 64;                                // u16 magnitudes incl. the extra pair-slots
-        WP = steps + 1;
-        nw = (T + 31) / 32;
-        size_t o = (size_t)(MPc + 8) * 2;
-        o = (o + 15) & ~(size_t)15;
-        off_dd = o;                                   // float2 first differences, 204 pair-slots per half block
-        dd_words = 2 * kQuarterPad * (2 * ((steps + 1) / 2) + 1);   // half of the tile per P1/P2 pass
-        if (dd_words < kFieldItems * 5)               // later reused as the P4 field buffer
-            dd_words = kFieldItems * 5;
-        o += (size_t)dd_words * 4;
-        off_planes = o;                               // S[phi][rho][word], de-interleaved mod 12
-        o += (size_t)5 * 12 * WP * 4;
-        edge_bytes = round_up(MPc / 8 + 16, 16);
-        o = (o + 15) & ~(size_t)15;
-        off_edges = o;                                // R then F: one bit per sample, consecutive
-        o += (size_t)2 * edge_bytes;
-        off_surv = o;
-        o += (size_t)nw * 4;
-        off_tabs = off_lut = 0;                       // tables live in global memory (L1)
-        off_queue = o;
-        o += (size_t)5 * kQueueCap * 2;
-        off_cand = o;
-        o += (size_t)kCandCap * 2;
-        bytes = (o + 15) & ~(size_t)15;
-    }
+    const uint32_t *tails;     // two stream tails of kTailWords each; counters[C_TAILCUR] selects the current one
 };
 
 // ------------------------------------------------------------------ magnitude
@@ -453,43 +396,34 @@ __device__ __forceinline__ unsigned long long event_first(const uint32_t *ev_key
 // walks one residue class (i = 12q + rho, q = 32 consecutive) reads d[i..i+2] with plain
 // strides and 32 consecutive (block, rho) items hit 32 different banks.
 
-// eight consecutive IQ words of a buffer starting at sample s (zero outside [0, len):
-// magnitude(0, 0) = 0 is exactly the MagnitudeBuffer zero fill, lib.rs:36-44)
-__device__ __forceinline__ uint32_t iq_word(const uint32_t *b32, int s, int len, const uint32_t *prev, int prev_len)
+// where the samples before a buffer come from in carry mode (B200ADSB_OPT_CARRY): the previous
+// buffers of the batch, then the stream tail saved by the previous batch
+struct CarrySrc {
+    const uint32_t *in;        // whole batch (buffer 0 of the batch, not of the launch)
+    unsigned long long stride;
+    const uint32_t *lengths;
+    uint32_t spb;
+    const uint32_t *tails;     // the two saved stream tails (last kTrailing samples before this batch)
+    const uint32_t *counters;  // [C_TAILCUR] selects the current tail
+    int on;
+};
+// IQ word of sample s of batch buffer b; s < 0 reaches back into the stream (carry mode) or is
+// zero (magnitude(0, 0) = 0 is exactly the MagnitudeBuffer zero fill, lib.rs:36-44); s >= len is zero
+__device__ __forceinline__ uint32_t iq_word(const uint32_t *b32, int s, int len, const CarrySrc &cs, uint32_t b)
 {
     if (s >= 0)
         return s < len ? __ldg(b32 + s) : 0u;
-    const int k = prev_len + s;          // carry mode: sample s < 0 lives in the previous buffer
-    return (prev != nullptr && k >= 0) ? __ldg(prev + k) : 0u;
-}
-__device__ __forceinline__ void load_iq8(const uint32_t *b32, int s, int len, int vec_ok, const uint32_t *prev,
-                                         int prev_len, uint32_t w[8])
-{
-    if (s >= 0 && s + 7 < len && vec_ok) {
-        const int4 v0 = __ldg(reinterpret_cast<const int4 *>(b32 + s));
-        const int4 v1 = __ldg(reinterpret_cast<const int4 *>(b32 + s + 4));
-        w[0] = (uint32_t)v0.x; w[1] = (uint32_t)v0.y; w[2] = (uint32_t)v0.z; w[3] = (uint32_t)v0.w;
-        w[4] = (uint32_t)v1.x; w[5] = (uint32_t)v1.y; w[6] = (uint32_t)v1.z; w[7] = (uint32_t)v1.w;
-    } else {
-#pragma unroll
-        for (int e = 0; e < 8; e++)
-            w[e] = iq_word(b32, s + e, len, prev, prev_len);
+    if (!cs.on)
+        return 0u;
+    while (b > 0) {            // buffers shorter than the reach-back are walked through
+        b--;
+        const int pl = cs.lengths ? (int)min(cs.lengths[b], cs.spb) : (int)cs.spb;
+        s += pl;
+        if (s >= 0)
+            return __ldg(cs.in + (unsigned long long)b * cs.stride + (unsigned)s);
     }
-}
-// the buffer whose tail supplies the samples before buffer b in carry mode
-__device__ __forceinline__ const uint32_t *carry_source(const void *in, unsigned long long stride,
-                                                        const uint32_t *lengths, uint32_t spb, uint32_t b,
-                                                        int carry, const uint32_t *tail, int *prev_len)
-{
-    *prev_len = 0;
-    if (!carry)
-        return nullptr;
-    if (b == 0) {
-        *prev_len = kTrailing;
-        return tail;
-    }
-    *prev_len = lengths ? (int)min(lengths[b - 1], spb) : (int)spb;
-    return reinterpret_cast<const uint32_t *>(in) + (unsigned long long)(b - 1) * stride;
+    const int k = kTrailing + s;
+    return k >= 0 ? cs.tails[kTailWords * (cs.counters[C_TAILCUR] & 1u) + k] : 0u;
 }
 
 // SNR and quiet-zone gates of one template match (demod_2400.rs:129,135-146) with the
@@ -539,443 +473,6 @@ __device__ __forceinline__ void gate_eval(const uint16_t *mag, uint32_t *surv, i
 __device__ __forceinline__ uint32_t df_of_fields(const uint32_t f[5])
 {
     return ((f[0] & 1u) << 4) | ((f[1] & 1u) << 3) | ((f[2] & 1u) << 2) | ((f[3] & 1u) << 1) | (f[4] & 1u);
-}
-
-template <bool FROM_MAG>
-__global__ void __launch_bounds__(kThreads, B200_SCAN_MIN_BLOCKS) scan_kernel(const ScanParams p)
-{
-    extern __shared__ __align__(16) unsigned char smem[];
-    const ScanParams &L = p;   // layout fields
-    uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
-    u64x *dd2 = reinterpret_cast<u64x *>(smem + L.off_dd);                  // (A, B) first-difference pairs
-    uint32_t *fb = reinterpret_cast<uint32_t *>(smem + L.off_dd);           // P4: staged fields (dd2 is dead)
-    const uint32_t *lut = p.lut;                                             // [12][5][5] field extraction table
-    uint32_t *planes = reinterpret_cast<uint32_t *>(smem + L.off_planes);   // [5][12][WP]
-    uint8_t *Rc = smem + L.off_edges;                 // rising-edge bit of every sample (bit i <-> m[i] < m[i+1])
-    uint8_t *Fc = Rc + L.edge_bytes;                  // falling-edge bit
-    uint32_t *surv = reinterpret_cast<uint32_t *>(smem + L.off_surv);
-    const uint32_t *tabs = p.crc_tabs;
-    uint16_t *queue = reinterpret_cast<uint16_t *>(smem + L.off_queue);     // [5][kQueueCap]
-    uint16_t *cand = reinterpret_cast<uint16_t *>(smem + L.off_cand);
-    __shared__ uint32_t s_warp_tot[kWarps];
-    __shared__ uint32_t s_base, s_count, s_ok, s_qn[5], s_nlong, s_nshort;
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
-    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
-    const int k = (int)(tile - b * (uint32_t)p.tiles_per_buffer);
-    const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
-    const int tile_start = k * p.T;
-    if (tile_start >= len) {
-        if (tid == 0)
-            p.tile_dir[tile] = make_uint2(0u, 0u);
-        return;
-    }
-    const int npos = min(p.T, len - tile_start);
-    const int steps = (npos + kHaloTot + kStep - 1) / kStep;   // 384-blocks actually needed
-    const int WP = L.WP;
-
-    // ---- P1/P2 in two passes over the tile (so that the first-difference buffer holds half
-    // of it and four thread blocks fit one SM).
-    // Pair-slot s holds sample s of stream A (tile samples [0, 192H)) and sample 192H+s of
-    // stream B.  Pass `ps` covers the half blocks [hb0, hb0+nh) of both streams.
-    const int H = steps;
-    const int offB = kHalf * H;
-    const int Hh = (H + 1) / 2;
-    int prev_len;
-    const uint32_t *prev = FROM_MAG ? nullptr
-                                    : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
-    for (int c = tid; c < L.nw; c += kThreads)
-        surv[c] = 0;
-    for (int c = tid; c < 5 * 12; c += kThreads)
-        planes[c * WP + steps] = 0;   // pad word read by funnel shifts
-    if (tid < 5)
-        s_qn[tid] = 0;
-    for (int ps = 0; ps < 2; ps++) {
-        const int hb0 = ps * Hh, nh = min(Hh, H - hb0);
-        if (nh <= 0)
-            break;
-        // ---- P1: magnitudes (u16), edge bits and first differences -> shared memory.  A warp
-        // takes 248 new pair-slots per iteration, 8 per lane (2 x 2 LDG.128); lane 31 recomputes
-        // the next chunk's first 8 only to hand lane 30 its right neighbour.
-        {
-            const int sl0 = kHalf * hb0, own_end = kHalf * (hb0 + nh);
-            const int nslots = kHalf * nh + 16;   // + right neighbours / pad mirror of the last half block
-            const int nchunk = (nslots + kChunk - 1) / kChunk;
-            const int s0 = tile_start - (kTrailing + kHaloFront);   // sample index of m[0]
-            const int i0 = tile_start - kHaloFront;                  // data index of m[0]
-            const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
-            const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
-            for (int ch = warp; ch < nchunk; ch += kWarps) {
-                const int rel = ch * kChunk + 8 * lane;   // pair-slot relative to this pass
-                const int sl = sl0 + rel;
-                u64x r[9];   // (A, B) pairs of f32 bit patterns 0x4B000000 + magnitude = 2^23 + magnitude
-                if (!FROM_MAG) {
-                    uint32_t wa[8], wb[8];
-                    load_iq8(b32, s0 + sl, len, p.vec_ok, prev, prev_len, wa);
-                    load_iq8(b32, s0 + offB + sl, len, p.vec_ok, prev, prev_len, wb);
-#pragma unroll
-                    for (int e = 0; e < 8; e++)
-                        r[e] = mag_pair_fast2(wa[e], wb[e]);
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const int ia = i0 + sl + e, ib = ia + offB;
-                        const uint32_t ma = (ia >= 0 && ia < kMagLen) ? (uint32_t)__ldg(d16 + ia) : 0u;
-                        const uint32_t mb = (ib >= 0 && ib < kMagLen) ? (uint32_t)__ldg(d16 + ib) : 0u;
-                        r[e] = f2_pack(__uint_as_float(0x4B000000u + ma), __uint_as_float(0x4B000000u + mb));
-                    }
-                }
-                r[8] = __shfl_down_sync(0xffffffffu, r[0], 1);
-                if (lane < 31 && rel < nslots) {
-                    u64x dv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; e++)
-                        dv[e] = f2_sub(r[e + 1], r[e]);      // m[i+1]-m[i], exact
-                    if (sl < own_end) {   // the 16 extra pair-slots belong to the next pass / tile
-                        uint32_t ra[8], rb[8];
-                        uint32_t fA = 0, fB = 0, rA_ = 0, rB_ = 0;
-#pragma unroll
-                        for (int e = 0; e < 8; e++) {
-                            float x, y;
-                            f2_unpack(r[e], x, y);
-                            ra[e] = __float_as_uint(x);
-                            rb[e] = __float_as_uint(y);
-                        }
-                        // edge bits of these samples (demod_2400.rs:221-317 compares neighbours only)
-#pragma unroll
-                        for (int e = 7; e >= 0; e--) {
-                            float x, y, nx, ny;
-                            f2_unpack(dv[e], x, y);
-                            f2_unpack(f2_sub(r[e], r[e + 1]), nx, ny);
-                            fA = __funnelshift_l(__float_as_uint(x), fA, 1);     // m[i+1]-m[i] < 0: falling
-                            fB = __funnelshift_l(__float_as_uint(y), fB, 1);
-                            rA_ = __funnelshift_l(__float_as_uint(nx), rA_, 1);  // rising
-                            rB_ = __funnelshift_l(__float_as_uint(ny), rB_, 1);
-                        }
-                        *reinterpret_cast<uint4 *>(mag + sl) =
-                            make_uint4(__byte_perm(ra[0], ra[1], 0x5410), __byte_perm(ra[2], ra[3], 0x5410),
-                                       __byte_perm(ra[4], ra[5], 0x5410), __byte_perm(ra[6], ra[7], 0x5410));
-                        *reinterpret_cast<uint4 *>(mag + offB + sl) =
-                            make_uint4(__byte_perm(rb[0], rb[1], 0x5410), __byte_perm(rb[2], rb[3], 0x5410),
-                                       __byte_perm(rb[4], rb[5], 0x5410), __byte_perm(rb[6], rb[7], 0x5410));
-                        Fc[sl >> 3] = (uint8_t)fA;
-                        Rc[sl >> 3] = (uint8_t)rA_;
-                        Fc[(offB + sl) >> 3] = (uint8_t)fB;
-                        Rc[(offB + sl) >> 3] = (uint8_t)rB_;
-                    }
-                    const int qb = rel / kQuarter, off = rel - qb * kQuarter;   // quarter block inside this pass
-                    u64x *dst = dd2 + kQuarterPad * qb + off;
-#pragma unroll
-                    for (int e = 0; e < 8; e += 2)
-                        *reinterpret_cast<ulonglong2 *>(dst + e) = make_ulonglong2(dv[e], dv[e + 1]);
-                    if (off < 12 && qb > 0) {   // mirror into the previous quarter block's pad
-                        u64x *pad = dd2 + kQuarterPad * (qb - 1) + kQuarter + off;
-                        *reinterpret_cast<ulonglong2 *>(pad) = make_ulonglong2(dv[0], dv[1]);
-                        *reinterpret_cast<ulonglong2 *>(pad + 2) = make_ulonglong2(dv[2], dv[3]);
-                        if (off == 0) {
-                            *reinterpret_cast<ulonglong2 *>(pad + 4) = make_ulonglong2(dv[4], dv[5]);
-                            *reinterpret_cast<ulonglong2 *>(pad + 6) = make_ulonglong2(dv[6], dv[7]);
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-        // ---- P2: correlator sign planes.  One lane = 8 samples at stride 12 (residue class rho,
-        // steps 8*sub..8*sub+7) of half block hb of stream A and of stream B, processed as
-        // (A, B) pairs in the packed f32x2 pipe; sign bits are shifted in with funnel shifts.
-        // demod_2400.rs:72-83 on negated first differences u,v,w (so that "x > 0" is a sign bit):
-        //   -[5,-3,-2] = 5u+2v   -[4,-1,-3] = 4u+3v   -[3,1,-4] = 3u+4v   -[2,3,-5] = 2u+5v
-        //   -[1,5,-5,-1] = u+6v+w      (all exact in f32: |.| < 2^20)
-        {
-            const u64x five = f2_pack(5.0f, 5.0f);
-            uint8_t *pbytes = reinterpret_cast<uint8_t *>(planes);
-            for (int task = tid; task < 24 * nh; task += kThreads) {
-                const int qb = task / 12, rho = task - 12 * qb;
-                const u64x *dp = dd2 + kQuarterPad * qb + rho;
-                uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0;
-#pragma unroll
-                for (int q = 7; q >= 0; q--) {
-                    const u64x u = dp[12 * q], v = dp[12 * q + 1], w = dp[12 * q + 2];
-                    const u64x g = f2_sub(v, u);
-                    const u64x x0 = f2_fma(u, five, f2_add(v, v));
-                    const u64x x1 = f2_add(x0, g), x2 = f2_add(x1, g), x3 = f2_add(x2, g);
-                    const u64x x4 = f2_add(f2_add(x3, g), w);
-                    float lo, hi;
-                    f2_unpack(x0, lo, hi);
-                    a0 = __funnelshift_l(__float_as_uint(lo), a0, 1);
-                    b0 = __funnelshift_l(__float_as_uint(hi), b0, 1);
-                    f2_unpack(x1, lo, hi);
-                    a1 = __funnelshift_l(__float_as_uint(lo), a1, 1);
-                    b1 = __funnelshift_l(__float_as_uint(hi), b1, 1);
-                    f2_unpack(x2, lo, hi);
-                    a2 = __funnelshift_l(__float_as_uint(lo), a2, 1);
-                    b2 = __funnelshift_l(__float_as_uint(hi), b2, 1);
-                    f2_unpack(x3, lo, hi);
-                    a3 = __funnelshift_l(__float_as_uint(lo), a3, 1);
-                    b3 = __funnelshift_l(__float_as_uint(hi), b3, 1);
-                    f2_unpack(x4, lo, hi);
-                    a4 = __funnelshift_l(__float_as_uint(lo), a4, 1);
-                    b4 = __funnelshift_l(__float_as_uint(hi), b4, 1);
-                }
-                // stream bit q = 8*(2*hb0 + qb) + step: one byte per task and stream
-                uint8_t *pa = pbytes + 4 * (rho * WP) + 2 * hb0 + qb, *pb = pa + 2 * H;
-                const int pstride = 4 * 12 * WP;
-                pa[0 * pstride] = (uint8_t)a0; pb[0 * pstride] = (uint8_t)b0;
-                pa[1 * pstride] = (uint8_t)a1; pb[1 * pstride] = (uint8_t)b1;
-                pa[2 * pstride] = (uint8_t)a2; pb[2 * pstride] = (uint8_t)b2;
-                pa[3 * pstride] = (uint8_t)a3; pb[3 * pstride] = (uint8_t)b3;
-                pa[4 * pstride] = (uint8_t)a4; pb[4 * pstride] = (uint8_t)b4;
-            }
-        }
-        __syncthreads();
-    }
-
-    // ---- P3a: preamble templates on the edge bitmaps, 32 consecutive positions per thread;
-    // matches go to one queue per template case
-    {
-        const uint32_t *R32 = reinterpret_cast<const uint32_t *>(Rc), *F32 = reinterpret_cast<const uint32_t *>(Fc);
-        const int nwp = (npos + kHaloFront + 31) / 32;
-        for (int w = tid; w < nwp; w += kThreads) {
-            // valid positions: 2 <= mi < npos+2 with mi = 32w + bit
-            const int lo = max(kHaloFront - 32 * w, 0), hi = min(npos + kHaloFront - 32 * w, 32);
-            const uint32_t valid = (hi - lo == 32) ? 0xffffffffu : (((1u << (hi - lo)) - 1u) << lo);
-            const uint32_t r0 = R32[w], r1 = R32[w + 1], f0 = F32[w], f1 = F32[w + 1];
-#define EDGE_R(s) __funnelshift_r(r0, r1, s)
-#define EDGE_F(s) __funnelshift_r(f0, f1, s)
-            const uint32_t quick = r0 & EDGE_F(12) & valid;   // demod_2400.rs:221
-            if (!quick)
-                continue;
-            const uint32_t F1 = EDGE_F(1), F2 = EDGE_F(2), F3 = EDGE_F(3), F4 = EDGE_F(4), F9 = EDGE_F(9),
-                           F10 = EDGE_F(10);
-            const uint32_t R2 = EDGE_R(2), R3 = EDGE_R(3), R8 = EDGE_R(8), R9 = EDGE_R(9), R10 = EDGE_R(10),
-                           R11 = EDGE_R(11);
-#undef EDGE_R
-#undef EDGE_F
-            // demod_2400.rs:226-317, in order; first match wins
-            const uint32_t T3 = F1 & R2 & F3 & R8 & F9 & R10;
-            const uint32_t T4 = F1 & R2 & F3 & R8 & F9 & R11;
-            const uint32_t T5 = F1 & R2 & F4 & R8 & F10 & R11;
-            const uint32_t T6 = F1 & R3 & F4 & R9 & F10 & R11;
-            const uint32_t T7 = F2 & R3 & F4 & R9 & F10 & R11;
-            uint32_t any = quick & (T3 | T4 | T5 | T6 | T7);
-            if (!any)
-                continue;
-            // case number as three bit planes: 0:T3 1:T4 2:T5 3:T6 4:T7
-            const uint32_t c1 = T4 & ~T3, c2 = T5 & ~(T3 | T4), c3 = T6 & ~(T3 | T4 | T5),
-                           c4 = ~(T3 | T4 | T5 | T6);
-            const uint32_t b0 = c1 | c3, b1 = c2 | c3;
-            while (any) {
-                const int bit = __ffs(any) - 1;
-                any &= any - 1;
-                const uint32_t cs = ((b0 >> bit) & 1u) | (((b1 >> bit) & 1u) << 1) | (((c4 >> bit) & 1u) << 2);
-                const int mi = 32 * w + bit;
-                const uint32_t qi = atomicAdd(&s_qn[cs], 1u);
-                if (qi < (uint32_t)kQueueCap)
-                    queue[cs * kQueueCap + qi] = (uint16_t)mi;
-                else
-                    gate_eval(mag, surv, mi, cs);     // queue full: evaluate in place
-            }
-        }
-    }
-    __syncthreads();
-    // ---- P3b: SNR and quiet-zone gates, one queue entry per thread, queues back to back
-    {
-        int n[5], tot = 0;
-#pragma unroll
-        for (int c = 0; c < 5; c++) {
-            n[c] = (int)min(s_qn[c], (uint32_t)kQueueCap);
-            tot += n[c];
-        }
-        for (int g = tid; g < tot; g += kThreads) {
-            int cs = 0, idx = g;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                if (cs == c && idx >= n[c]) {
-                    idx -= n[c];
-                    cs = c + 1;
-                }
-            gate_eval(mag, surv, (int)queue[cs * kQueueCap + idx], (uint32_t)cs);
-        }
-    }
-    __syncthreads();
-
-    // ---- P4a: count survivors, reserve pool space (positions are emitted in ascending j)
-    uint32_t wv = (tid < L.nw) ? surv[tid] : 0u;   // nw <= 256 == kThreads
-    int my_off;
-    {
-        const int cnt = __popc(wv);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        if (lane == 31)
-            s_warp_tot[warp] = (uint32_t)incl;
-        __syncthreads();
-        my_off = incl - cnt;
-        uint32_t total = 0;
-#pragma unroll
-        for (int wi = 0; wi < kWarps; wi++) {
-            const uint32_t t = s_warp_tot[wi];
-            if (wi < warp)
-                my_off += (int)t;
-            total += t;
-        }
-        if (tid == 0) {
-            uint32_t base = 0, ok = 1;
-            if (total) {
-                base = atomicAdd(&p.counters[C_POOL], total);
-                if (base + total > p.pool_cap || base + total < base) {
-                    atomicOr(&p.counters[C_FLAGS], F_POOL_OVF);
-                    ok = 0;
-                }
-                atomicAdd(&p.counters[C_CAND], total);
-            }
-            p.tile_dir[tile] = make_uint2(base, ok ? total : 0u);
-            s_base = base;
-            s_count = total;
-            s_ok = ok;
-            s_nlong = 0;
-            s_nshort = 0;
-        }
-    }
-    __syncthreads();
-    if (!s_ok || s_count == 0)
-        return;
-
-    // ---- P4b: five try-phases per survivor, in windows of kCandCap survivors.
-    //   A: pull the five 23-bit fields of each (survivor, try_phase) out of the sign planes,
-    //      read the DF; items that need a CRC are staged by class (112-bit / 56-bit syndrome)
-    //   B: CRC-24 + classification on class-homogeneous runs -> record words + ICAO add-events
-    const int C = (int)s_count;
-    const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
-    for (int win = 0; win < C; win += kCandCap) {
-        {
-            uint32_t wv2 = wv;
-            int off = my_off;
-            while (wv2) {
-                const int bit = __ffs(wv2) - 1;
-                wv2 &= wv2 - 1;
-                if (off >= win && off < win + kCandCap)
-                    cand[off - win] = (uint16_t)(tid * 32 + bit);
-                off++;
-            }
-        }
-        __syncthreads();
-        const int Cw = min(kCandCap, C - win);
-        uint32_t *rec_w = p.rec + 6ull * (s_base + (uint32_t)win);
-        for (int item = tid; item < 5 * Cw; item += kThreads) {
-            const int c = item / 5, tt = item - 5 * c;
-            const int jl = cand[c];
-            // demod_2400.rs:158-160: P0 = 5*(mi+19) + try_phase, try_phase = 4+tt
-            const int A = jl + kHaloFront + 19;
-            const int qA = A / 12, rA = A - 12 * qA;
-            const uint32_t *lrow = lut + 25 * rA + 5 * tt;
-            uint32_t f[5];
-#pragma unroll
-            for (int r = 0; r < 5; r++) {
-                const uint32_t e = __ldg(lrow + r);
-                const int q = qA + (int)(e >> 16);
-                const uint32_t *st = planes + (e & 0xffffu) + (q >> 5);
-                f[r] = __funnelshift_r(st[0], st[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
-            }
-            if (tt == 0)
-                rec_w[6 * c] = (uint32_t)(tile_start + jl);
-            // class of the item: 0 = decided here, 1 = needs the 112-bit syndrome, 2 = the 56-bit one
-            uint32_t wd = 0;
-            int cls = 0;
-            if ((f[0] | f[1] | f[2] | f[3] | f[4]) == 0) {
-                wd = kNoneMarker;                      // all 14 bytes zero -> None (mode_s/mod.rs:51-53)
-            } else {
-                const uint32_t bit = 1u << df_of_fields(f);
-                if (bit & 0xFF370000u)                 // DF 16,17,18,20,21,24..31
-                    cls = 1;
-                else if (bit & 0x00000831u)            // DF 0,4,5,11
-                    cls = 2;
-            }
-#if B200_AGG_ATOMICS
-            // one shared-memory atomic per warp and class instead of one per item
-            const unsigned act = __activemask();
-            const unsigned ml = __ballot_sync(act, cls == 1), ms = __ballot_sync(act, cls == 2);
-            const int leader = __ffs(act) - 1;
-            uint32_t basel = 0, bases = 0;
-            if (lane == leader) {
-                if (ml)
-                    basel = atomicAdd(&s_nlong, (uint32_t)__popc(ml));
-                if (ms)
-                    bases = atomicAdd(&s_nshort, (uint32_t)__popc(ms));
-            }
-            basel = __shfl_sync(act, basel, leader);
-            bases = __shfl_sync(act, bases, leader);
-            const unsigned lt = (1u << lane) - 1u;
-#endif
-            if (cls) {
-#if B200_AGG_ATOMICS
-                const uint32_t slot = cls == 1 ? basel + (uint32_t)__popc(ml & lt)
-                                               : (uint32_t)(kFieldItems - 1) - (bases + (uint32_t)__popc(ms & lt));
-#else
-                const uint32_t slot = cls == 1 ? atomicAdd(&s_nlong, 1u)
-                                               : (uint32_t)(kFieldItems - 1) - atomicAdd(&s_nshort, 1u);
-#endif
-                uint32_t *o = fb + 5 * slot;
-                o[0] = f[0];
-                o[1] = f[1];
-                o[2] = f[2] | (((uint32_t)item & 0x3ffu) << 22);
-                o[3] = f[3] | (((uint32_t)item >> 10) << 22);
-                o[4] = f[4];
-            } else {
-                rec_w[6 * c + 1 + tt] = wd;
-            }
-        }
-        __syncthreads();
-        {
-            const int nl = (int)s_nlong, ns = (int)s_nshort;
-            for (int g = tid; g < nl + ns; g += kThreads) {
-                const bool is_long = g < nl;
-                const uint32_t slot = is_long ? (uint32_t)g : (uint32_t)(kFieldItems - 1 - (g - nl));
-                const uint32_t *o = fb + 5 * slot;
-                uint32_t f[5] = {o[0], o[1], o[2], o[3], o[4]};
-                const int item = (int)((f[2] >> 22) | ((f[3] >> 22) << 10));
-                f[2] &= 0x3fffffu;
-                f[3] &= 0x3fffffu;
-                const uint32_t df = df_of_fields(f);
-                uint32_t wd;
-                if (is_long) {
-                    const uint32_t syn = syn112_fields(tabs, f);
-                    if (df == 17 || df == 18)          // mode_s/mod.rs:91-109
-                        wd = syn ? 0u : (((df == 17 ? K_DF17 : K_DF18) << 29) | msg_bits<8, 24>(f));
-                    else                                // :110-134
-                        wd = (K_PAR_LONG << 29) | syn;
-                } else {
-                    const uint32_t syn = syn56_fields(tabs, f);
-                    if (df == 11)                       // :73-90
-                        wd = (syn & 0xffff80u) ? 0u
-                                               : ((((syn & 0x7f) ? K_DF11_IID : K_DF11_IID0) << 29) | msg_bits<8, 24>(f));
-                    else                                // :56-72
-                        wd = (K_PAR_SHORT << 29) | syn;
-                }
-                const int c = item / 5, tt = item - 5 * c;
-                rec_w[6 * c + 1 + tt] = wd;
-                const uint32_t kind = wd >> 29;
-                if (kind == K_DF11_IID0 || kind == K_DF17 || kind == K_DF18) {
-                    const uint32_t key = (wd & 0xffffffu) | (kind == K_DF18 ? B200ADSB_ICAO_FILTER_ADSB_NT : 0u);
-                    const uint32_t j = (uint32_t)(tile_start + cand[c]);
-                    event_add(p.ev_keys, p.ev_ord, p.ev_used, p.ev_mask, p.counters, key,
-                              ord_buf | ((unsigned long long)j << 3) | (unsigned long long)tt);
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            s_nlong = 0;
-            s_nshort = 0;
-        }
-    }
 }
 
 // ================================================================== to_mag kernel
@@ -1055,15 +552,22 @@ __global__ void events_export_kernel(const uint32_t *ev_keys, const unsigned lon
         pairs[2ull * i + 1] = ev_ord[h];
     }
 }
-// packed form for a sync-free exchange: rows[0] = (count, 0), rows[1..] = (key, ordinal)
+// packed form for a sync-free exchange: rows[0] = (count, this rank's bad-batch flags),
+// rows[1..] = (key, ordinal).  A rank with more events than the exchange buffer holds fails its own
+// batch too (F_EV_OVF), so that every rank takes the same decision.
 __global__ void events_pack_kernel(const uint32_t *ev_keys, const unsigned long long *ev_ord,
-                                   const uint32_t *ev_used, const uint32_t *counters,
+                                   const uint32_t *ev_used, uint32_t *counters,
                                    unsigned long long *rows, uint32_t rows_cap)
 {
     const uint32_t n = counters[C_EV_USED];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t fl = counters[C_FLAGS] & kBadMask;
+        if (n > rows_cap - 1) {
+            fl |= F_EV_OVF;
+            atomicOr(&counters[C_FLAGS], F_EV_OVF);
+        }
         rows[0] = n;
-        rows[1] = 0;
+        rows[1] = fl;
     }
     const uint32_t m = min(n, rows_cap - 1);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
@@ -1072,7 +576,8 @@ __global__ void events_pack_kernel(const uint32_t *ev_keys, const unsigned long 
         rows[2ull * (i + 1) + 1] = ev_ord[h];
     }
 }
-// gathered: n_ranks blocks of rows_per_rank packed rows; merges every block but `skip`
+// gathered: n_ranks blocks of rows_per_rank packed rows; merges every block but `skip` (this rank's
+// own); a bad batch on any rank makes this rank's batch bad too (F_REMOTE_BAD)
 __global__ void events_import_packed_kernel(const unsigned long long *gathered, uint32_t n_ranks,
                                             uint32_t rows_per_rank, uint32_t skip, uint32_t *ev_keys,
                                             unsigned long long *ev_ord, uint32_t *ev_used, uint32_t mask,
@@ -1083,9 +588,9 @@ __global__ void events_import_packed_kernel(const unsigned long long *gathered, 
             continue;
         const unsigned long long *rows = gathered + 2ull * r * rows_per_rank;
         const unsigned long long n = rows[0];
-        if (n > rows_per_rank - 1) {   // that rank had more events than fit the exchange buffer
+        if (n > rows_per_rank - 1 || (rows[1] & kBadMask) != 0ull) {
             if (blockIdx.x == 0 && threadIdx.x == 0)
-                atomicOr(&counters[C_FLAGS], F_EV_OVF);
+                atomicOr(&counters[C_FLAGS], F_REMOTE_BAD);
             continue;
         }
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += gridDim.x * blockDim.x)
@@ -1184,14 +689,22 @@ __global__ void __launch_bounds__(1024) events_finalize_kernel(const FinalizeArg
                          a.bloom);
 }
 
-// after resolve: the admitted keys join the filter; the event table is recycled
+// after resolve: the admitted keys join the filter; the event table is recycled.
+// A bad batch (candidate pool / event table / exchange buffer overflow here or on another rank) is
+// not committed: nothing of it may reach the filter, the host redoes it.  Enqueue-only batches
+// (d_result != nullptr) additionally honour and raise the sticky flag: once a queued batch failed,
+// the batches queued behind it are not committed either -- they would otherwise run against a
+// filter that lacks the failed batch's addresses and then leave their own in it, which no re-run
+// could undo -- until the host acknowledges (b200adsb_async_acknowledge or any synchronous call).
+// flip_tail: carry mode, the tail saved by this batch becomes the stream tail.
 __device__ __forceinline__ void events_commit_body(uint32_t *ev_keys, unsigned long long *ev_ord,
                                                    const uint32_t *ev_used, const uint32_t *new_keys,
-                                                   uint32_t *counters, uint32_t *members)
+                                                   uint32_t *counters, uint32_t *members, uint32_t *d_result,
+                                                   uint32_t cap, int flip_tail)
 {
-    // a scan that overflowed the candidate pool or the event table is redone by the host:
-    // nothing of it may reach the filter
-    const bool bad = (counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF)) != 0;
+    const uint32_t fl = counters[C_FLAGS];
+    const bool sticky = d_result != nullptr && counters[C_STICKY] != 0u;
+    const bool bad = (fl & kBadMask) != 0u || sticky;
     const uint32_t n = counters[C_EV_USED], adm = bad ? 0u : counters[C_ADMIT];
     for (uint32_t i = threadIdx.x; i < adm; i += blockDim.x)
         members_insert(members, new_keys[i]);
@@ -1206,25 +719,33 @@ __device__ __forceinline__ void events_commit_body(uint32_t *ev_keys, unsigned l
         counters[C_EV_USED] = 0;
         counters[C_ADMIT] = 0;
         counters[C_NEWCNT] = 0;
+        if (flip_tail && !bad)
+            counters[C_TAILCUR] ^= 1u;
+        if (d_result) {       // enqueue-only batch outcome; the per-batch counters are cleared here
+            d_result[0] = bad ? 0u : counters[C_FRAMES];
+            d_result[1] = (fl & kBadMask) | (sticky ? F_SKIPPED : 0u);
+            d_result[2] = counters[C_CAND];
+            d_result[3] = counters[C_FRAMES] > cap ? 1u : 0u;
+            if (bad)
+                counters[C_STICKY] = 1u;
+            counters[C_POOL] = 0;
+            counters[C_FLAGS] = 0;
+            counters[C_CAND] = 0;
+        }
     }
 }
-// d_result (nullable): the enqueue-only batch outcome {frames, overflow flags, candidates,
-// frames > cap}; the per-batch counters are then cleared here instead of by host memsets
-__global__ void __launch_bounds__(1024) events_commit_kernel(uint32_t *ev_keys, unsigned long long *ev_ord,
-                                                             const uint32_t *ev_used, const uint32_t *new_keys,
-                                                             uint32_t *counters, uint32_t *members,
-                                                             uint32_t *d_result = nullptr, uint32_t cap = 0)
+struct CommitArgs {
+    uint32_t *ev_keys;
+    unsigned long long *ev_ord;
+    const uint32_t *ev_used, *new_keys;
+    uint32_t *counters, *members, *d_result;
+    uint32_t cap;
+    int flip_tail;
+};
+__global__ void __launch_bounds__(1024) events_commit_kernel(const CommitArgs a)
 {
-    events_commit_body(ev_keys, ev_ord, ev_used, new_keys, counters, members);
-    if (d_result && threadIdx.x == 0) {
-        d_result[0] = counters[C_FRAMES];
-        d_result[1] = counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF);
-        d_result[2] = counters[C_CAND];
-        d_result[3] = counters[C_FRAMES] > cap ? 1u : 0u;
-        counters[C_POOL] = 0;
-        counters[C_FLAGS] = 0;
-        counters[C_CAND] = 0;
-    }
+    events_commit_body(a.ev_keys, a.ev_ord, a.ev_used, a.new_keys, a.counters, a.members, a.d_result, a.cap,
+                       a.flip_tail);
 }
 
 // ================================================================== resolve
@@ -1421,7 +942,8 @@ struct EmitParams {
     const uint32_t *tile_cnt;    // frames per tile
     const uint32_t *cta_excl;    // exclusive prefix per block of 32 tiles
     int carry;
-    const uint32_t *tail;
+    const uint32_t *tails;     // carry mode: the two stream tails
+    const uint32_t *counters;  //             and [C_TAILCUR]
     uint32_t n_tiles;
     int tiles_per_buffer;
     b200adsb_frame *out;
@@ -1455,9 +977,8 @@ __device__ __forceinline__ void emit_body(const EmitParams &p, const uint32_t bl
     const uint2 d = p.tile_dir[tile];
     const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
     const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
-    int prev_len = 0;
-    const uint32_t *prev = (FROM_MAG || p.msgs) ? nullptr
-                                                : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
+    const CarrySrc cs{reinterpret_cast<const uint32_t *>(p.in), p.stride, p.lengths, p.spb, p.tails, p.counters,
+                      (FROM_MAG || p.msgs) ? 0 : p.carry};
     for (uint32_t base = 0; base < my_cnt; base += 32) {
         const uint32_t i = base + lane;
         const uint32_t info = i < my_cnt ? p.emit_info[d.x + i] : 0u;
@@ -1481,7 +1002,7 @@ __device__ __forceinline__ void emit_body(const EmitParams &p, const uint32_t bl
                         const uint32_t *bb = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
                         const int s = idx - kTrailing;
                         // == mag_pair (exhaustively checked)
-                        m = mag_bits_fast(iq_word(bb, s, len, prev, prev_len)) & 0xffffu;
+                        m = mag_bits_fast(iq_word(bb, s, len, cs, b)) & 0xffffu;
                     }
                     s_mag[warp][k] = (uint16_t)m;
                 }
@@ -1547,25 +1068,10 @@ constexpr int kEmitWarps = 8;
 // The commit step has no data dependency on the emit step (it touches the filter, the event table and
 // other counter words), so it rides along as the last block of this launch instead of a launch of
 // its own.
-struct CommitArgs {
-    uint32_t *ev_keys;
-    unsigned long long *ev_ord;
-    const uint32_t *ev_used, *new_keys;
-    uint32_t *counters, *members, *d_result;
-    uint32_t cap;
-};
 __device__ __forceinline__ void commit_tail(const CommitArgs &a)
 {
-    events_commit_body(a.ev_keys, a.ev_ord, a.ev_used, a.new_keys, a.counters, a.members);
-    if (a.d_result && threadIdx.x == 0) {      // enqueue-only batch outcome, per-batch counters cleared
-        a.d_result[0] = a.counters[C_FRAMES];
-        a.d_result[1] = a.counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF);
-        a.d_result[2] = a.counters[C_CAND];
-        a.d_result[3] = a.counters[C_FRAMES] > a.cap ? 1u : 0u;
-        a.counters[C_POOL] = 0;
-        a.counters[C_FLAGS] = 0;
-        a.counters[C_CAND] = 0;
-    }
+    events_commit_body(a.ev_keys, a.ev_ord, a.ev_used, a.new_keys, a.counters, a.members, a.d_result, a.cap,
+                       a.flip_tail);
 }
 template <bool FROM_MAG>
 __global__ void __launch_bounds__(32 * kEmitWarps) emit_frames_kernel(const EmitParams p, const uint32_t *counters,
@@ -1610,9 +1116,8 @@ __global__ void __launch_bounds__(32 * kEmitWarps) emit_frames_kernel(const Emit
         const uint2 d = p.tile_dir[tile];
         const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
         const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
-        int prev_len = 0;
-        const uint32_t *prev = (FROM_MAG || p.msgs) ? nullptr
-                                                    : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
+        const CarrySrc cs{reinterpret_cast<const uint32_t *>(p.in), p.stride, p.lengths, p.spb, p.tails, p.counters,
+                          (FROM_MAG || p.msgs) ? 0 : p.carry};
         const uint32_t inf = p.emit_info[d.x + i];
         const uint32_t j = p.rec[6ull * (d.x + ((inf >> 4) & 0x1fffu))];
         const int t = 4 + (int)(inf & 7u), flen = (inf & 8u) ? 14 : 7;
@@ -1627,7 +1132,7 @@ __global__ void __launch_bounds__(32 * kEmitWarps) emit_frames_kernel(const Emit
                         m = dd[idx];
                 } else {
                     const uint32_t *bb = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
-                    m = mag_bits_fast(iq_word(bb, idx - kTrailing, len, prev, prev_len)) & 0xffffu;   // == mag_pair
+                    m = mag_bits_fast(iq_word(bb, idx - kTrailing, len, cs, b)) & 0xffffu;   // == mag_pair
                 }
                 s_mag[warp][k] = (uint16_t)m;
             }
@@ -1684,7 +1189,8 @@ __global__ void __launch_bounds__(32 * kEmitWarps) emit_frames_kernel(const Emit
 // microseconds each would dominate the call.
 template <bool FROM_MAG>
 __global__ void __launch_bounds__(kResolveThreads) resolve_small_kernel(const FinalizeArgs fa, const ResolveParams rp,
-                                                                        const EmitParams ep, const uint32_t n_ctas)
+                                                                        const EmitParams ep, const uint32_t n_ctas,
+                                                                        const int flip_tail)
 {
     events_finalize_body(fa.ev_keys, fa.ev_ord, fa.ev_used, fa.ev_tmp, fa.new_keys, fa.counters, fa.members,
                          fa.ev_mask, fa.bloom);
@@ -1698,17 +1204,20 @@ __global__ void __launch_bounds__(kResolveThreads) resolve_small_kernel(const Fi
         emit_body<FROM_MAG>(ep, blk);
         __syncthreads();
     }
-    events_commit_body(fa.ev_keys, fa.ev_ord, fa.ev_used, fa.new_keys, fa.counters, fa.members);
+    events_commit_body(fa.ev_keys, fa.ev_ord, fa.ev_used, fa.new_keys, fa.counters, fa.members, nullptr, 0u, flip_tail);
 }
 
 // carry mode: the last 326 samples of the stream (walking back over this batch's buffers,
 // then into the old tail) become the next batch's leading samples
 __global__ void save_tail_kernel(const uint32_t *in, unsigned long long stride, const uint32_t *lengths,
-                                 uint32_t spb, uint32_t n_buffers, const uint32_t *old_tail, uint32_t *new_tail)
+                                 uint32_t spb, uint32_t n_buffers, uint32_t *tails, const uint32_t *counters)
 {
     const int k = threadIdx.x;
     if (k >= kTrailing)
         return;
+    const uint32_t cur = counters[C_TAILCUR] & 1u;
+    const uint32_t *old_tail = tails + kTailWords * cur;
+    uint32_t *new_tail = tails + kTailWords * (cur ^ 1u);   // becomes current when the batch commits
     int back = kTrailing - 1 - k;          // 0 = the very last sample of the stream
     uint32_t w = 0;
     bool found = false;

@@ -37,7 +37,7 @@ constexpr int k7GroupsPerWarp = 10;         // 30 of 32 lanes
 constexpr int k7GroupsPerPass = k7GroupsPerWarp * k7Warps;
 constexpr int k7CandCap = 128;              // survivors decoded per window
 constexpr int k7FieldItems = 5 * k7CandCap;
-constexpr int k7ListCap = 1024;             // template matches gated per round
+constexpr int k7ListCap = 1024;             // template matches gated per round (at most; see Scan7Smem::list_cap)
 #ifndef B200_SCAN7_MIN_BLOCKS
 #define B200_SCAN7_MIN_BLOCKS 7
 #endif
@@ -47,10 +47,13 @@ constexpr int k7ListCap = 1024;             // template matches gated per round
 #ifndef B200_SCAN7_RING
 #define B200_SCAN7_RING 3                   // IQ rows in flight per lane (cp.async ring); 0: register prefetch
 #endif
+#ifndef B200_SCAN7_LIST_ALIAS
+#define B200_SCAN7_LIST_ALIAS 0             // 1: the match list lives in the edge planes (dead after the template pass)
+#endif
 
 // shared memory plan for tile size T
 struct Scan7Smem {
-    int NG, WP, nw, mag_len;
+    int NG, WP, nw, mag_len, list_cap;
     size_t off_planes, off_surv, off_masks, off_list, off_cand, bytes;
     __host__ __device__ explicit Scan7Smem(int T)
     {
@@ -72,8 +75,14 @@ struct Scan7Smem {
             const size_t ring_b = (size_t)k7Threads * B200_SCAN7_RING * 16, mask_b = (size_t)12 * WP * 16;
             o += ring_b > mask_b ? ring_b : mask_b;
         }
+#if B200_SCAN7_LIST_ALIAS
+        off_list = off_planes + (size_t)5 * 12 * WP * 4;   // rising + falling planes: 2 * 12 * WP words
+        list_cap = 48 * WP < k7ListCap ? 48 * WP : k7ListCap;
+#else
         off_list = o;
         o += (size_t)k7ListCap * 2;
+        list_cap = k7ListCap;
+#endif
         off_cand = o;
         o += (size_t)k7CandCap * 2;
         bytes = (o + 15) & ~(size_t)15;
@@ -83,7 +92,7 @@ struct Scan7Smem {
 struct Scan7Params {
     ScanParams s;
     uint32_t off_planes, off_surv, off_masks, off_list, off_cand;
-    int NG, WP, nw;
+    int NG, WP, nw, list_cap;
     int Wrow, inv_Wrow;    // mask words per residue row for this tile size; ceil(65536 / Wrow): i / Wrow == (i * inv) >> 16 for i < 12 * Wrow
 };
 
@@ -94,7 +103,7 @@ struct Row {
 
 template <bool FROM_MAG>
 __device__ __noinline__ Row row_slow(const ScanParams &p, const uint32_t *b32, const uint16_t *d16, int s,
-                                        int i, int len, const uint32_t *prev, int prev_len)
+                                        int i, int len, const CarrySrc &cs, uint32_t b)
 {
     Row r;
     if (!FROM_MAG) {
@@ -105,7 +114,7 @@ __device__ __noinline__ Row row_slow(const ScanParams &p, const uint32_t *b32, c
         } else {
 #pragma unroll
             for (int e = 0; e < 4; e++)
-                w[e] = iq_word(b32, s + e, len, prev, prev_len);
+                w[e] = iq_word(b32, s + e, len, cs, b);
         }
         r.q0 = mag_pair_fast2(w[0], w[2]);
         r.q1 = mag_pair_fast2(w[1], w[3]);
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
 #endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile = blockIdx.x;
+    const uint32_t tile = p.b0 * (uint32_t)p.tiles_per_buffer + blockIdx.x;   // tile of the batch
     const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
     const int kt = (int)(tile - b * (uint32_t)p.tiles_per_buffer);
     const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
@@ -319,9 +328,8 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
 
     // ---- P1: dense phase (magnitudes, edges, correlator signs; see the header)
     {
-        int prev_len = 0;
-        const uint32_t *prev = FROM_MAG ? nullptr
-                                        : carry_source(p.in, p.stride, p.lengths, p.spb, b, p.carry, p.tail, &prev_len);
+        const CarrySrc cs{reinterpret_cast<const uint32_t *>(p.in), p.stride, p.lengths, p.spb, p.tails, p.counters,
+                          FROM_MAG ? 0 : p.carry};
         const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
         const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
         const int s0 = tile_start - (kTrailing + kHaloFront);    // sample index of tile magnitude 0
@@ -351,7 +359,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                     rbnd.q0 = mag_pair_fast2((uint32_t)v.x, (uint32_t)v.z);
                     rbnd.q1 = mag_pair_fast2((uint32_t)v.y, (uint32_t)v.w);
                 } else {
-                    rbnd = row_slow<FROM_MAG>(p, b32, d16, s0 + rb, i0 + rb, len, prev, prev_len);
+                    rbnd = row_slow<FROM_MAG>(p, b32, d16, s0 + rb, i0 + rb, len, cs, b);
                 }
                 float x, y;
                 f2_unpack(rbnd.q0, st.pm0, st.pm2);
@@ -393,30 +401,28 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                     mrow -= 12;
                 }
 #else
-                // running pointers, two slots per iteration (no register rotation), one row of prefetch
+                // plain LDG.128 with one row of register prefetch, one slot per iteration
                 const int4 *src = reinterpret_cast<const int4 *>(b32 + s0 + r0) + 3 * (k7Slots - 1);
-                int4 va = __ldg(src), vb;
+                int4 v = __ldg(src);
 #pragma unroll 1
-                for (int k = k7Slots / 2 - 1; k >= 0; k--) {
-                    vb = __ldg(src - 3);
-                    Row r;
-                    r.q0 = mag_pair_fast2((uint32_t)va.x, (uint32_t)va.z);
-                    r.q1 = mag_pair_fast2((uint32_t)va.y, (uint32_t)va.w);
-                    dense_slot(st, r, is_c0, src_lane, mrow, own);
-                    src -= 6;
+                for (int k = k7Slots - 1; k >= 0; k--) {
+                    src -= 3;
+                    int4 nv = v;
                     if (k > 0)
-                        va = __ldg(src);
-                    r.q0 = mag_pair_fast2((uint32_t)vb.x, (uint32_t)vb.z);
-                    r.q1 = mag_pair_fast2((uint32_t)vb.y, (uint32_t)vb.w);
-                    dense_slot(st, r, is_c0, src_lane, mrow - 12, own);
-                    mrow -= 24;
+                        nv = __ldg(src);
+                    Row r;
+                    r.q0 = mag_pair_fast2((uint32_t)v.x, (uint32_t)v.z);
+                    r.q1 = mag_pair_fast2((uint32_t)v.y, (uint32_t)v.w);
+                    dense_slot(st, r, is_c0, src_lane, mrow, own);
+                    mrow -= 12;
+                    v = nv;
                 }
 #endif
             } else {
 #pragma unroll 1
                 for (int k = k7Slots - 1; k >= 0; k--) {
                     const int rr = r0 + 12 * k;
-                    const Row r = row_slow<FROM_MAG>(p, b32, d16, s0 + rr, i0 + rr, len, prev, prev_len);
+                    const Row r = row_slow<FROM_MAG>(p, b32, d16, s0 + rr, i0 + rr, len, cs, b);
                     dense_slot(st, r, is_c0, src_lane, mrow, own);
                     mrow -= 12;
                 }
@@ -484,14 +490,14 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             while (any) {
                 const int bit = __ffs(any) - 1;
                 any &= any - 1;
-                if (off < k7ListCap)
+                if (off < P.list_cap)
                     list[off] = (uint16_t)(i | (bit << 10));       // (mask word, bit); the gate thread decodes
                 off++;
             }
         }
     }
     __syncthreads();
-    if (s_count > (uint32_t)k7ListCap) {
+    if (s_count > (uint32_t)P.list_cap) {
         // more matches than the list holds (pathological input): gate every match in place.  Matches
         // that also made it into the list are evaluated twice, which is harmless (a gate only sets a bit).
         const uint4 *min4 = reinterpret_cast<const uint4 *>(masks);
@@ -510,7 +516,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     // ---- P3c: SNR and quiet-zone gates, one match per thread
     {
         const uint4 *min4 = reinterpret_cast<const uint4 *>(masks);
-        const int n = min((int)s_count, k7ListCap);
+        const int n = min((int)s_count, P.list_cap);
         for (int g = tid; g < n; g += k7Threads) {
             const uint32_t e = list[g];
             const int i = (int)(e & 0x3ffu), bit = (int)(e >> 10);

@@ -151,15 +151,21 @@ int b200adsb_demod_iq_batch_dev(b200adsb_ctx *ctx, const int16_t *d_iq, size_t n
  * consumer of the frames on the device or reading them later): the call returns as soon as
  * the batch is queued on the context's stream; nothing is read back.  d_result (device,
  * 4 x uint32): [0] frames written to d_out in (buffer, j) order, [1] 0, or non-zero when
- * the optimistic candidate pool / event table overflowed -- that batch was NOT committed to
- * the filter and wrote no valid frames: rerun it (and the batches queued after it) with the
- * synchronous call, which grows the pool; [2] positions that passed the preamble gates;
- * [3] 1 when more than `cap` frames were found.  Batches on one context execute in call
+ * the batch failed -- bit 0: the optimistic candidate pool overflowed, bit 1: the event table /
+ * exchange buffer overflowed, bit 4: another rank of a sharded stream failed its batch, bit 3: an
+ * EARLIER queued batch failed and has not been acknowledged.  A failed batch is NOT committed to
+ * the filter and wrote no valid frames, and neither is any batch queued behind it (their d_result[1]
+ * has bit 3 set), so the filter is exactly what it was before the first failed batch: rerun that batch
+ * and the ones queued after it with the synchronous call (which grows the pool and acknowledges the
+ * failure; b200adsb_async_acknowledge does only the latter); [2] positions that passed the preamble
+ * gates; [3] 1 when more than `cap` frames were found.  Batches on one context execute in call
  * order with one filter, exactly like the synchronous form. */
 int b200adsb_demod_iq_batch_dev_async(b200adsb_ctx *ctx, const int16_t *d_iq, size_t n_buffers,
                                       size_t samples_per_buffer, size_t stride_samples,
                                       const uint32_t *d_lengths, b200adsb_frame *d_out, size_t cap,
                                       uint32_t *d_result);
+
+int b200adsb_async_acknowledge(b200adsb_ctx *ctx);
 
 /* ---- split form for a stream sharded over several GPUs (one context per rank).
  * scan:    stage 1 on this rank's buffers; local buffer b has stream ordinal
@@ -175,9 +181,11 @@ int b200adsb_events_count(b200adsb_ctx *ctx, size_t *n);
 /* pairs: 2*cap u64 in DEVICE memory: (key, ordinal) per event */
 int b200adsb_events_export_dev(b200adsb_ctx *ctx, uint64_t *d_pairs, size_t cap, size_t *n);
 int b200adsb_events_import_dev(b200adsb_ctx *ctx, const uint64_t *d_pairs, size_t n);
-/* the same exchange without host round trips: rows[0] = (count, 0), rows[1..] = (key, ordinal);
- * all-gather the fixed-size row blocks, then merge every block but this rank's own.  A rank
- * with more than rows-1 events makes the later resolve fail with B200ADSB_ERR_EVENTS. */
+/* the same exchange without host round trips: rows[0] = (count, bad-batch flags of this rank),
+ * rows[1..] = (key, ordinal); all-gather the fixed-size row blocks, then merge every block but
+ * this rank's own.  A rank with more than rows-1 events, or whose scan overflowed, fails the batch
+ * on EVERY rank (itself included): the later resolve returns B200ADSB_ERR_EVENTS / reports it in
+ * d_result[1], and no rank commits -- the ranks' filters stay identical. */
 int b200adsb_events_pack_dev(b200adsb_ctx *ctx, uint64_t *d_rows, size_t rows_cap);
 int b200adsb_events_import_packed_dev(b200adsb_ctx *ctx, const uint64_t *d_gathered, size_t n_ranks,
                                       size_t rows_per_rank, size_t skip_rank);
@@ -214,6 +222,18 @@ int b200adsb_modes_checksum(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n, 
 int b200adsb_score_modes_messages(b200adsb_ctx *ctx, const uint8_t *msgs14, size_t n,
                                   uint8_t *lens, int32_t *scores);
 
+/* The same two with the reference's own shapes, one message per call (thin wrappers over the batched
+ * forms; the context stands for the process-wide filter):
+ *   modes_checksum(message: &[u8], bits: usize) -> u32                 (src/crc.rs:263-282)
+ *   score_modes_message(msg: &[u8]) -> Option<(MsgLen, i32)>           (src/mode_s/mod.rs:34-139)
+ *       *msglen = 7 / 14, or 0 for None (then *score is 0)
+ *   getbits(data, firstbit_1idx, lastbit_1idx)  (pure, host)           (src/mode_s/mod.rs:14-30) */
+int b200adsb_modes_checksum_one(b200adsb_ctx *ctx, const uint8_t *msg, size_t n_bytes, size_t bits,
+                                uint32_t *out);
+int b200adsb_score_modes_message(b200adsb_ctx *ctx, const uint8_t *msg, size_t n_bytes, int *msglen,
+                                 int *score);
+uint32_t b200adsb_getbits(const uint8_t *data, size_t firstbit_1idx, size_t lastbit_1idx);
+
 /* ------------------------------------------------------- dump1090_rs/src/main.rs:174-176 */
 /* "*{hex};\n" per frame, the AVR text the reference binary sends to its TCP clients (host
  * formatting only; the listener itself is out of scope).  *len = bytes needed/written. */
@@ -222,6 +242,13 @@ int b200adsb_format_avr(const b200adsb_frame *frames, size_t n, char *out, size_
 /* test hook: exhaustive GPU comparison of the scan kernel's fast magnitude arithmetic
  * with the IEEE-intrinsic statement of src/utils.rs:47-55 over all 2^32 inputs. */
 int b200adsb_debug_mag_sweep(b200adsb_ctx *ctx, uint64_t *mismatches, uint32_t *first_bad);
+
+/* test hook: the stage-1 records of the pending batch, valid between b200adsb_scan_batch_dev and
+ * b200adsb_resolve_batch_dev: for every position that passed the preamble gates
+ * (src/demod_2400.rs:127-146), in (buffer, j) order, its batch buffer index and the six words
+ * {j, w[0..5)}, w[t-4] = kind<<29 | key of try-phase t (the stateless part of
+ * src/mode_s/mod.rs:34-139; kinds as in oracle/dump1090_oracle.h). */
+int b200adsb_debug_records(b200adsb_ctx *ctx, uint32_t *buffers, uint32_t *rec6, size_t cap, size_t *n);
 
 /* test hook, pure host: the 840-word CRC-24 field tables used by the scan kernel
  * followed by the 256-entry byte table (src/crc.rs:3-260); returns 840. */

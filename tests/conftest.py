@@ -22,6 +22,9 @@ def pytest_configure(config):
     if not (os.path.exists(so) and os.path.exists(orc)):
         import __graft_entry__ as g
         g.build()
+    else:
+        from dump1090_rs_b200 import _ffi
+        _ffi.build()          # no-op when the library is newer than every csrc/*.cu, *.cuh and the header
 
 
 @pytest.fixture(scope="session")

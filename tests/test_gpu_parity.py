@@ -549,3 +549,174 @@ def test_dense_template_matches_overflow_the_match_list(pkg, ctx, oracle_mod):
     assert frames_key(got) == frames_key(ref)
     assert len(ref) > 0
     assert ctx.timing()["candidates"] == n_surv
+
+
+# ---------------------------------------------------------------- round 2: per-stage parity, recovery paths
+def _norm_words(ws):
+    """kind NONE carries no key worth comparing (the kernel marks `None` with key 1, the oracle with 0)."""
+    return [0 if (w >> 29) == 0 else w for w in ws]
+
+
+def _stage1_records(pkg, iq_batch, tile=None):
+    """(buffer, j, words) of every position that passed the gates, through the split scan call."""
+    import torch
+    from dump1090_rs_b200 import _ffi
+    nb, spb = iq_batch.shape[0], iq_batch.shape[1]
+    c = pkg.Context(0)
+    if tile:
+        c.set_option(_ffi.OPT_TILE, tile)
+    d_iq = torch.from_numpy(np.ascontiguousarray(iq_batch)).to("cuda:0")
+    c.scan_batch_dev(d_iq.data_ptr(), nb, spb, spb, 0, 1)
+    recs = c.debug_records()
+    out = torch.zeros((4096, 28), dtype=torch.uint8, device="cuda:0")
+    c.resolve_batch_dev(out.data_ptr(), 4096)
+    c.close()
+    return [(b, j, _norm_words(w)) for b, j, w in recs]
+
+
+@pytest.mark.parametrize("tile", [None, 1624, 472])
+def test_stage1_records_equal_oracle_on_captures(tile, pkg, captures, oracle_mod):
+    """the survivor set of the preamble gates (demod_2400.rs:127-146) and
+    the stateless classification of every (j, try_phase) (demod_2400.rs:158-189, mode_s/mod.rs:34-139)
+    equal orc_demod_records -- including the ~1400 candidates per capture that never become frames."""
+    batch = np.stack([captures[n] for n in NAMES])
+    got = _stage1_records(pkg, batch, tile)
+    o = oracle_mod.Oracle()
+    ref = []
+    for b, n in enumerate(NAMES):
+        ref += [(b, j, _norm_words(w)) for j, w in o.records(o.to_mag(captures[n]))]
+    assert len(ref) > 3000
+    assert got == ref
+
+
+def test_stage1_records_dense_pattern_and_full_range(pkg, oracle_mod):
+    from dump1090_rs_b200 import synth
+    pat = np.array([3, 8, 11, 4, 11, 1, 4, 9, 8, 1, 11])
+    n = 131072
+    a = synth.make_batch(5, 1, msgs_per_buffer=20)[0].copy()
+    part = n // 8
+    levels = np.tile(pat, part // len(pat) + 1)[:part]
+    a[:part, 0] = (250 * levels + 100).astype(np.int16)
+    a[:part, 1] = 0
+    b = synth.full_range_buffer(3, 0)
+    c = synth.make_batch(9, 1, msgs_per_buffer=100)[0]
+    batch = np.stack([a, b, c])
+    got = _stage1_records(pkg, batch)
+    o = oracle_mod.Oracle()
+    ref = []
+    for k in range(3):
+        ref += [(k, j, _norm_words(w)) for j, w in o.records(o.to_mag(batch[k]), cap=1 << 17)]
+    assert len(ref) > 10000
+    assert got == ref
+
+
+def test_carry_with_h2d_chunks_and_short_buffers(pkg, oracle_mod):
+    """Carry mode through the host batch call when the batch is scanned in several H2D chunks
+    (the chunk's first buffer continues the batch, not the previous batch) and with buffers
+    shorter than the 326-sample reach-back (walked through several buffers)."""
+    from dump1090_rs_b200 import _ffi, synth
+    stream, _ = synth.make_buffer(41, 0, n=120000, msgs_per_buffer=110, icao_pool=6)
+    rng = np.random.default_rng(7)
+    for case, (spb, chunk) in enumerate([(6000, 1), (6000, 3), (2500, 2)]):
+        nb = 120000 // spb
+        lens = [spb] * nb
+        for k in rng.choice(nb, size=nb // 3, replace=False):      # ragged, some very short buffers
+            lens[int(k)] = int(rng.choice([0, 1, 50, 200, 325, 326, 327, 1000, spb - 1]))
+        batch = np.zeros((nb, spb, 2), dtype=np.int16)
+        bufs, pos = [], 0
+        for b in range(nb):
+            bufs.append(stream[pos:pos + lens[b]])
+            batch[b, :lens[b]] = bufs[-1]
+            pos += lens[b]
+        o = oracle_mod.Oracle()
+        ref = []
+        for b in range(nb):
+            for f in o.demod_iq_carry(bufs[b]):
+                f["buffer"] = b
+                ref.append(f)
+        assert len(ref) > 20
+        c = pkg.Context(0)
+        c.set_option(_ffi.OPT_CARRY, 1)
+        c.set_option(_ffi.OPT_H2D_CHUNK, chunk)
+        half = nb // 2                                              # two calls: the tail crosses calls too
+        got = c.demod_iq_batch(batch[:half], half, spb, lengths=lens[:half])
+        for f in c.demod_iq_batch(batch[half:], nb - half, spb, lengths=lens[half:]):
+            f["buffer"] += half
+            got.append(f)
+        assert frames_key(got) == frames_key(ref), (case, spb, chunk)
+        c.close()
+
+
+def test_enqueue_only_overflow_is_sticky_and_recoverable(pkg, oracle_mod):
+    """A queued batch that overflows the candidate pool is not committed, and neither are the batches
+    queued behind it (d_result[1] bit 3): the filter stays what it was, and re-running them with the
+    synchronous call reproduces the reference."""
+    import torch
+    from dump1090_rs_b200 import _ffi, synth
+    spb, cap = 131072, 4096
+    quiet = synth.make_batch(21, 2, msgs_per_buffer=8, icao_pool=4)
+    later = synth.make_batch(22, 2, msgs_per_buffer=8, icao_pool=4)          # same aircraft pool
+    pat = np.array([3, 8, 11, 4, 11, 1, 4, 9, 8, 1, 11])
+    dense = synth.make_batch(23, 2, msgs_per_buffer=8, icao_pool=4).copy()
+    levels = np.tile(pat, spb // len(pat) + 1)[:spb]
+    dense[0, :, 0] = (250 * levels + 100).astype(np.int16)
+    dense[0, :, 1] = 0
+    batches = [quiet, dense, later]
+    ref, o = oracle_stream(oracle_mod, [b for batch in batches for b in batch])
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(b)).to(dev) for b in batches]
+    stream = torch.cuda.current_stream()
+    ctx = pkg.Context(0, stream.cuda_stream)
+    frames = torch.zeros((3, cap, 28), dtype=torch.uint8, device=dev)
+    res = torch.zeros((3, 4), dtype=torch.int32, device=dev)
+    n0 = ctx.demod_iq_batch_ptr(d[0].data_ptr(), 2, spb, spb, frames[0].data_ptr(), cap)   # sizes the pool for quiet traffic
+    snap0 = sorted(ctx.icao_snapshot())
+    for k in (1, 2):
+        ctx.demod_iq_batch_async_ptr(d[k].data_ptr(), 2, spb, spb, frames[k].data_ptr(), cap, res[k].data_ptr())
+    ctx.sync()
+    r = res.cpu().numpy()
+    assert r[1, 1] & 1, r                  # the dense batch overflowed the pool
+    assert r[2, 1] & 8 and r[2, 0] == 0, r   # the batch behind it was skipped
+    assert sorted(ctx.icao_snapshot()) == snap0
+    counts = [n0]
+    for k in (1, 2):                       # recovery: the synchronous call, in order
+        counts.append(ctx.demod_iq_batch_ptr(d[k].data_ptr(), 2, spb, spb, frames[k].data_ptr(), cap))
+    # a later enqueue-only batch commits again
+    ctx.demod_iq_batch_async_ptr(d[0].data_ptr(), 2, spb, spb, frames[0].data_ptr(), cap, res[0].data_ptr())
+    ctx.sync()
+    assert res.cpu().numpy()[0, 1] == 0
+    got = []
+    for k in range(1, 3):
+        raw = frames[k, :counts[k]].cpu().numpy()
+        for row in raw:
+            got.append((2 * k + int(row[24:28].view(np.uint32)[0]), int(row[20:24].view(np.uint32)[0]), int(row[15]),
+                        int(row[16:18].view(np.int16)[0]), bytes(row[: row[14]]).hex()))
+    assert got == [t for t in frames_key(ref) if t[0] >= 2]
+    assert set(ctx.icao_snapshot()) == o.members()
+    ctx.close()
+
+
+def test_single_message_surface(pkg, ctx, oracle_mod, golden_frames):
+    """getbits / modes_checksum / score_modes_message with the reference's own shapes
+    (mode_s/mod.rs:14,34, crc.rs:263)."""
+    import ctypes as C
+    L = oracle_mod.lib()
+    rng = np.random.default_rng(3)
+    msgs = [bytes.fromhex(g["hex"]) for n in NAMES for g in golden_frames[n]]
+    for m in msgs:
+        assert pkg.crc.modes_checksum(m, 8 * len(m), ctx) == oracle_mod.modes_checksum(m, 8 * len(m))
+        for a, b in [(1, 5), (9, 32), (33, 56), (1, 1), (8 * len(m), 8 * len(m))]:
+            buf = (C.c_uint8 * len(m)).from_buffer_copy(m)
+            assert pkg.mode_s.getbits(m, a, b) == L.orc_getbits(buf, a, b)
+    o = oracle_mod.Oracle()
+    ctx.icao_flush()
+    seq = msgs + [bytes(14), bytes(7), bytes([0x28]) + bytes(5), msgs[0][:7], bytes(rng.integers(0, 256, 14, dtype=np.uint8))] + msgs
+    for m in seq:
+        buf = (C.c_uint8 * max(len(m), 1)).from_buffer_copy(m.ljust(1, b"\0"))
+        ln, sc = C.c_int(0), C.c_int(0)
+        ok = L.orc_score_modes_message(C.byref(o.filter), buf, len(m), C.byref(ln), C.byref(sc))
+        got = pkg.mode_s.score_modes_message(m, ctx)
+        if not ok:
+            assert got is None, m.hex()
+        else:
+            assert got is not None and (14 if got[0] == pkg.demod_2400.MsgLen.Long else 7, got[1]) == (ln.value, sc.value), m.hex()
