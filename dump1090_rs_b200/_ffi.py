@@ -127,6 +127,7 @@ _PROTOS = {
     "b200adsb_async_acknowledge": (C.c_int, [C.c_void_p]),
     "b200adsb_debug_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "b200adsb_debug_crc_tabs": (C.c_int, [C.c_void_p]),
+    "b200adsb_debug_crc_lane_tabs": (C.c_int, [C.c_void_p]),
     "b200adsb_debug_mag_sweep": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]),
 }
 

@@ -54,9 +54,10 @@ struct b200adsb_ctx {
     uint32_t *d_members = nullptr;
     uint32_t *d_ev_keys = nullptr, *d_ev_used = nullptr, *d_ev_tmp = nullptr, *d_new_keys = nullptr;
     unsigned long long *d_ev_ord = nullptr;
-    uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr, *d_lut = nullptr;
+    uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr, *d_lut = nullptr, *d_crc_lanes = nullptr;
     uint32_t h_lut[kLutWords];
     int lut_T = 0, lut_WP = 0;
+    int n_sms = 148;
     bool counters_clean = false;     // C_POOL/C_FLAGS/C_CAND already zero (cleared by the last commit kernel)
     uint32_t *d_scalar = nullptr;
 
@@ -109,7 +110,7 @@ uint32_t crc_pow(int e)   // x^e mod G, G = x^24 + 0xFFF409
 
 // Field tables of kernels.cuh::a112/a56: field bit m of field r is message bit 5m+r.
 //   a112(f) = sum_{m<=21} f[m] x^(107-5m),  a56(f) = sum_{m<=10} f[m] x^(51-5m)
-void build_crc_tabs(uint32_t *t, uint32_t *t256)
+void build_crc_tabs(uint32_t *t, uint32_t *t256, uint32_t *lanes = nullptr)
 {
     auto fill = [&](uint32_t *dst, int entries, int m0, int e_base) {
         for (int v = 0; v < entries; v++) {
@@ -125,6 +126,18 @@ void build_crc_tabs(uint32_t *t, uint32_t *t256)
     fill(t + 512, 64, 16, 107);
     fill(t + kTab56, 256, 0, 51);
     fill(t + kTab56 + 256, 8, 8, 51);
+    // the same sums as shuffle tables (kernels.cuh::a112_sh / a56_sh): 5-bit chunks of a field
+    if (lanes)
+        for (int v = 0; v < 32; v++)
+            for (int c = 0; c < kLaneTabs; c++) {
+                uint32_t sx = 0;
+                for (int bit = 0; bit < 5; bit++) {
+                    const int m = 5 * (c < 5 ? c : c - 5) + bit;
+                    if (((v >> bit) & 1) && (c < 5 ? m <= 21 : true))
+                        sx ^= crc_pow((c < 5 ? 107 : 51) - 5 * m);
+                }
+                lanes[32 * c + v] = sx;
+            }
     for (uint32_t i = 0; i < 256; i++) {   // src/crc.rs:3-260, generated from the polynomial
         uint32_t c = i << 16;
         for (int k = 0; k < 8; k++)
@@ -293,6 +306,12 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.T = q.T;
     p.tiles_per_buffer = q.tpb;
     p.vec_ok = (!q.from_mag && ((uintptr_t)q.in % 16 == 0) && (q.stride % 4 == 0)) ? 1 : 0;
+    {
+        int per_sm = 0;   // a host-side table lookup, not a device call
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan7_kernel<false>, k7Threads, L7.bytes) != cudaSuccess)
+            per_sm = 0;
+        p.pf_dist = (uint32_t)(per_sm * c->n_sms);
+    }
     p.rec = c->d_rec;
     p.pool_cap = (uint32_t)std::min<size_t>(c->pool_cap, 0xffffffffu);
     p.tile_dir = c->d_tile_dir;
@@ -304,6 +323,7 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.ord_first = q.ord_first;
     p.ord_stride = q.ord_stride;
     p.crc_tabs = c->d_crc_tabs;
+    p.crc_lanes = c->d_crc_lanes;
     p.lut = c->d_lut;
     p.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
     p.tails = c->d_tails;
@@ -644,6 +664,7 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
             return fail(B200ADSB_ERR_CUDA); \
     } while (0)
     CKC(cudaSetDevice(device));
+    CKC(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device));
     {   // the scan kernel's launch attributes, once: room for the largest tile, all of L1 as shared memory
         const int max_smem = (int)Scan7Smem(kMaxTile).bytes;
         CKC(cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -672,15 +693,17 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     CKC(cudaMalloc((void **)&c->d_new_keys, (size_t)B200ADSB_ICAO_FILTER_SIZE * 4));
     CKC(cudaMalloc((void **)&c->d_crc_tabs, kTabWords * 4));
     CKC(cudaMalloc((void **)&c->d_crc256, 256 * 4));
+    CKC(cudaMalloc((void **)&c->d_crc_lanes, kLaneTabs * 32 * 4));
     CKC(cudaMalloc((void **)&c->d_lut, kLutWords * 4));
     CKC(cudaMalloc((void **)&c->d_bloom, kBloomWords * 4));
     CKC(cudaMalloc((void **)&c->d_tails, 2 * kTailWords * 4));
     CKC(cudaMemset(c->d_tails, 0, 2 * kTailWords * 4));
     CKC(cudaMalloc((void **)&c->d_scalar, 64));
     {
-        uint32_t t[kTabWords], t256[256];
-        build_crc_tabs(t, t256);
+        uint32_t t[kTabWords], t256[256], tl[kLaneTabs * 32];
+        build_crc_tabs(t, t256, tl);
         CKC(cudaMemcpy(c->d_crc_tabs, t, sizeof t, cudaMemcpyHostToDevice));
+        CKC(cudaMemcpy(c->d_crc_lanes, tl, sizeof tl, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_crc256, t256, sizeof t256, cudaMemcpyHostToDevice));
     }
 #undef CKC
@@ -708,6 +731,7 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_new_keys);
     cudaFree(c->d_crc_tabs);
     cudaFree(c->d_crc256);
+    cudaFree(c->d_crc_lanes);
     cudaFree(c->d_lut);
     cudaFree(c->d_scalar);
     cudaFree(c->d_rec);
@@ -1459,6 +1483,16 @@ int b200adsb_debug_crc_tabs(uint32_t *out)
         return B200ADSB_ERR_BAD_ARG;
     build_crc_tabs(out, out + kTabWords);
     return kTabWords;
+}
+
+/* test hook (pure host): the per-lane shuffle form of the same tables, 7 x 32 u32 (kernels.cuh::a112_sh) */
+int b200adsb_debug_crc_lane_tabs(uint32_t *out)
+{
+    if (!out)
+        return B200ADSB_ERR_BAD_ARG;
+    uint32_t t[kTabWords], t256[256];
+    build_crc_tabs(t, t256, out);
+    return kLaneTabs * 32;
 }
 
 }  // extern "C"

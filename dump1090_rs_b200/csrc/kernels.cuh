@@ -72,6 +72,7 @@ struct ScanParams {
     unsigned long long stride; // IQ: samples between buffers; MAG: u16 elements
     int T, tiles_per_buffer;
     int vec_ok;                // 16-byte aligned base and stride % 4 == 0
+    uint32_t pf_dist;          // blocks resident at once on the device (L2 prefetch distance in tiles); 0: off
     uint32_t *rec;             // pool of 6-word records {j, w[5]}
     uint32_t pool_cap;
     uint2 *tile_dir;           // per tile of the batch: (pool base, count)
@@ -82,6 +83,7 @@ struct ScanParams {
     uint32_t ev_mask;
     unsigned long long ord_first, ord_stride;
     const uint32_t *crc_tabs;  // CRC-24 field tables (global memory, L1 resident)
+    const uint32_t *crc_lanes; // [kLaneTabs][32]: the same as per-lane shuffle tables (a112_sh / a56_sh)
     const uint32_t *lut;       // [12][5][5] field extraction table for this tile size
     // opt-in stream continuity (B200ADSB_OPT_CARRY): the 326 leading MagnitudeBuffer slots of a
     // buffer hold the previous buffer's last samples instead of zeros
@@ -269,6 +271,44 @@ __device__ __forceinline__ uint32_t syn56_fields(const uint32_t *t, const uint32
     s = mulx(s) ^ a56(t, f[4]);
     return s ^ ((f[0] >> 11) & 1u);                                 // bit 55
 }
+// The same field sums with the tables held in registers, one entry per lane, and looked up with warp
+// shuffles (5-bit chunks of the field: shfl takes the lane index modulo 32, so `f >> 5c` needs no mask).
+// A table lookup through L1 costs ~7 tag wavefronts per warp on the LSU pipe, a shuffle one; the LSU pipe is
+// the kernel's busiest unit (profiles/r2).  All 32 lanes must execute these together.
+//   lanes[c][v], c = 0..4: sum_{b<5, 5c+b<=21} v[b] x^(107-5(5c+b))      (long)
+//   lanes[5+c][v], c = 0..1: sum_{b<5} v[b] x^(51-5(5c+b))               (short; m = 10 is x^1 = 2)
+constexpr int kLaneTabs = 7;
+struct CrcLanes {
+    uint32_t t[kLaneTabs];
+};
+__device__ __forceinline__ uint32_t a112_sh(const CrcLanes &L, uint32_t f)
+{
+    return __shfl_sync(0xffffffffu, L.t[0], f) ^ __shfl_sync(0xffffffffu, L.t[1], f >> 5) ^
+           __shfl_sync(0xffffffffu, L.t[2], f >> 10) ^ __shfl_sync(0xffffffffu, L.t[3], f >> 15) ^
+           __shfl_sync(0xffffffffu, L.t[4], (f >> 20) & 3u);
+}
+__device__ __forceinline__ uint32_t a56_sh(const CrcLanes &L, uint32_t f)
+{
+    return __shfl_sync(0xffffffffu, L.t[5], f) ^ __shfl_sync(0xffffffffu, L.t[6], f >> 5) ^ (((f >> 10) & 1u) << 1);
+}
+__device__ __forceinline__ uint32_t syn112_fields_sh(const CrcLanes &L, const uint32_t f[5])
+{
+    uint32_t s = a112_sh(L, f[0]);
+    s = mulx(s) ^ a112_sh(L, f[1]);
+    s = mulx(s) ^ a112_sh(L, f[2]);
+    s = mulx(s) ^ a112_sh(L, f[3]);
+    s = mulx(s) ^ a112_sh(L, f[4]);
+    return s ^ (((f[0] >> 22) & 1u) << 1) ^ ((f[1] >> 22) & 1u);   // bits 110, 111
+}
+__device__ __forceinline__ uint32_t syn56_fields_sh(const CrcLanes &L, const uint32_t f[5])
+{
+    uint32_t s = a56_sh(L, f[0]);
+    s = mulx(s) ^ a56_sh(L, f[1]);
+    s = mulx(s) ^ a56_sh(L, f[2]);
+    s = mulx(s) ^ a56_sh(L, f[3]);
+    s = mulx(s) ^ a56_sh(L, f[4]);
+    return s ^ ((f[0] >> 11) & 1u);                                 // bit 55
+}
 // bits n0 .. n0+cnt-1 of the message, MSB first, from the five fields
 template <int N0, int CNT>
 __device__ __forceinline__ uint32_t msg_bits(const uint32_t f[5])
@@ -427,10 +467,10 @@ __device__ __forceinline__ uint32_t iq_word(const uint32_t *b32, int s, int len,
 }
 
 // SNR and quiet-zone gates of one template match (demod_2400.rs:129,135-146) with the
-// template's high/signal/noise (demod_2400.rs:226-317); cs = template case 0..4.
-__device__ __forceinline__ void gate_eval(const uint16_t *mag, uint32_t *surv, int mi, uint32_t cs)
+// template's high/signal/noise (demod_2400.rs:226-317); cs = template case 0..4; pp = the 19
+// magnitudes from the candidate position on, jl = its survivor bit.
+__device__ __forceinline__ void gate_eval(const uint16_t *pp, uint32_t *surv, int jl, uint32_t cs)
 {
-    const uint16_t *pp = mag + mi;
     int high;
     uint32_t sig, noise;
     switch (cs) {
@@ -466,7 +506,6 @@ __device__ __forceinline__ void gate_eval(const uint16_t *mag, uint32_t *surv, i
                        max(max(max((int)pp[14], (int)pp[15]), max((int)pp[16], (int)pp[17])), (int)pp[18]));
     if (mx >= high)            // demod_2400.rs:135-146
         return;
-    const int jl = mi - kHaloFront;
     atomicOr(&surv[jl >> 5], 1u << (jl & 31));
 }
 

@@ -253,6 +253,8 @@ int b200adsb_debug_records(b200adsb_ctx *ctx, uint32_t *buffers, uint32_t *rec6,
 /* test hook, pure host: the 840-word CRC-24 field tables used by the scan kernel
  * followed by the 256-entry byte table (src/crc.rs:3-260); returns 840. */
 int b200adsb_debug_crc_tabs(uint32_t *out);
+/* the same field sums as 7 tables of 32 entries for warp-shuffle lookup (5-bit chunks); returns 224 */
+int b200adsb_debug_crc_lane_tabs(uint32_t *out);
 
 #ifdef __cplusplus
 }

@@ -120,6 +120,54 @@ def test_crc_field_tables(oracle_mod):
         assert v == int.from_bytes(m[1:4], "big")
 
 
+def test_crc_lane_tables(oracle_mod):
+    """kernels.cuh syn112_fields_sh/syn56_fields_sh (tables held one entry per lane, looked up by warp
+    shuffle with the lane index taken modulo 32) == modes_checksum (crc.rs:263-282)."""
+    L = _ffi.lib()
+    lt = np.zeros(7 * 32, dtype=np.uint32)
+    assert L.b200adsb_debug_crc_lane_tabs(lt.ctypes.data) == 224
+    t = [[int(x) for x in lt[32 * c:32 * c + 32]] for c in range(7)]
+    sh = lambda c, idx: t[c][idx & 31]          # __shfl_sync(L.t[c], idx)
+    a112 = lambda f: sh(0, f) ^ sh(1, f >> 5) ^ sh(2, f >> 10) ^ sh(3, f >> 15) ^ sh(4, (f >> 20) & 3)
+    a56 = lambda f: sh(5, f) ^ sh(6, f >> 5) ^ (((f >> 10) & 1) << 1)
+    rng = np.random.default_rng(4)
+    msgs = [bytes(rng.integers(0, 256, 14, dtype=np.uint8)) for _ in range(3000)]
+    msgs += [bytes([0] * k + [1 << b] + [0] * (13 - k)) for k in range(14) for b in range(8)]
+    for m in msgs:
+        f = _fields(m)
+        s = a112(f[0])
+        for r in range(1, 5):
+            s = _mulx(s) ^ a112(f[r])
+        s ^= (((f[0] >> 22) & 1) << 1) ^ ((f[1] >> 22) & 1)
+        assert s == oracle_mod.modes_checksum(m, 112)
+        s = a56(f[0])
+        for r in range(1, 5):
+            s = _mulx(s) ^ a56(f[r])
+        s ^= (f[0] >> 11) & 1
+        assert s == oracle_mod.modes_checksum(m[:7], 56)
+
+
+def test_padded_magnitude_layout():
+    """scan7.cuh mag_pos: element i of a tile lives at 24 + i + 24*(i/192) (i/192 by multiply-shift), each
+    192-sample group is followed by a copy of the next group's first 24 elements, so a window of up to 24
+    consecutive elements addressed from its first element's group reads the right values."""
+    pad, grp = 24, 192
+    n = 8192
+    for i in range(n):
+        assert (i * 43691) >> 23 == i // grp
+    NG = 40
+    vals = np.arange(NG * grp, dtype=np.int64) + 1000
+    arr = np.full(pad + NG * (grp + pad) + 32, -1, dtype=np.int64)
+    for i in range(NG * grp):                        # what the dense phase stores
+        pos = pad + i + pad * (i // grp)
+        arr[pos] = vals[i]
+        if i % grp < 24:                             # slots 0 and 1 also write the copy
+            arr[pos - pad] = vals[i]
+    for i in range(NG * grp - 24):
+        base = pad + i + pad * (i // grp)
+        assert (arr[base:base + 24] == vals[i:i + 24]).all(), i
+
+
 def test_abi_exports_match_header():
     """Every function declared in include/b200adsb.h is exported by libb200adsb.so."""
     import os
