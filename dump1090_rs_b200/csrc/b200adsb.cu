@@ -54,10 +54,9 @@ struct b200adsb_ctx {
     uint32_t *d_members = nullptr;
     uint32_t *d_ev_keys = nullptr, *d_ev_used = nullptr, *d_ev_tmp = nullptr, *d_new_keys = nullptr;
     unsigned long long *d_ev_ord = nullptr;
-    uint32_t *d_crc_tabs = nullptr, *d_crc256 = nullptr, *d_lut = nullptr, *d_crc_lanes = nullptr;
+    uint32_t *d_crc256 = nullptr, *d_lut = nullptr, *d_crc_lanes = nullptr;
     uint32_t h_lut[kLutWords];
     int lut_T = 0, lut_WP = 0;
-    int n_sms = 148;
     bool counters_clean = false;     // C_POOL/C_FLAGS/C_CAND already zero (cleared by the last commit kernel)
     uint32_t *d_scalar = nullptr;
 
@@ -306,12 +305,6 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.T = q.T;
     p.tiles_per_buffer = q.tpb;
     p.vec_ok = (!q.from_mag && ((uintptr_t)q.in % 16 == 0) && (q.stride % 4 == 0)) ? 1 : 0;
-    {
-        int per_sm = 0;   // a host-side table lookup, not a device call
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan7_kernel<false>, k7Threads, L7.bytes) != cudaSuccess)
-            per_sm = 0;
-        p.pf_dist = (uint32_t)(per_sm * c->n_sms);
-    }
     p.rec = c->d_rec;
     p.pool_cap = (uint32_t)std::min<size_t>(c->pool_cap, 0xffffffffu);
     p.tile_dir = c->d_tile_dir;
@@ -322,7 +315,6 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     p.ev_mask = kEvSlots - 1;
     p.ord_first = q.ord_first;
     p.ord_stride = q.ord_stride;
-    p.crc_tabs = c->d_crc_tabs;
     p.crc_lanes = c->d_crc_lanes;
     p.lut = c->d_lut;
     p.carry = (c->carry && !q.from_mag && !q.msgs) ? 1 : 0;
@@ -572,8 +564,8 @@ int resolve_run_impl(b200adsb_ctx *c, b200adsb_frame *d_out, size_t cap, size_t 
     prof_end(c, c->other_events);
     int rc = read_counters(c);
     if (rc) { q.active = false; return rc; }
-    if (c->h_counters[C_FLAGS] & (F_POOL_OVF | F_EV_OVF))
-        return kRedo;   // optimistic scan overflowed: nothing was committed, the caller redoes it
+    if (c->h_counters[C_FLAGS] & kBadMask)
+        return kRedo;   // the batch failed (here or on another rank): nothing was committed, the caller redoes it
     q.active = false;
     c->timing.candidates += c->h_counters[C_CAND];
     const size_t n = c->h_counters[C_FRAMES];
@@ -664,7 +656,6 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
             return fail(B200ADSB_ERR_CUDA); \
     } while (0)
     CKC(cudaSetDevice(device));
-    CKC(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device));
     {   // the scan kernel's launch attributes, once: room for the largest tile, all of L1 as shared memory
         const int max_smem = (int)Scan7Smem(kMaxTile).bytes;
         CKC(cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
@@ -691,7 +682,6 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     CKC(cudaMalloc((void **)&c->d_ev_used, kEvSlots * 4));
     CKC(cudaMalloc((void **)&c->d_ev_tmp, kEvSlots * 4));
     CKC(cudaMalloc((void **)&c->d_new_keys, (size_t)B200ADSB_ICAO_FILTER_SIZE * 4));
-    CKC(cudaMalloc((void **)&c->d_crc_tabs, kTabWords * 4));
     CKC(cudaMalloc((void **)&c->d_crc256, 256 * 4));
     CKC(cudaMalloc((void **)&c->d_crc_lanes, kLaneTabs * 32 * 4));
     CKC(cudaMalloc((void **)&c->d_lut, kLutWords * 4));
@@ -702,7 +692,6 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     {
         uint32_t t[kTabWords], t256[256], tl[kLaneTabs * 32];
         build_crc_tabs(t, t256, tl);
-        CKC(cudaMemcpy(c->d_crc_tabs, t, sizeof t, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_crc_lanes, tl, sizeof tl, cudaMemcpyHostToDevice));
         CKC(cudaMemcpy(c->d_crc256, t256, sizeof t256, cudaMemcpyHostToDevice));
     }
@@ -729,7 +718,6 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_ev_used);
     cudaFree(c->d_ev_tmp);
     cudaFree(c->d_new_keys);
-    cudaFree(c->d_crc_tabs);
     cudaFree(c->d_crc256);
     cudaFree(c->d_crc_lanes);
     cudaFree(c->d_lut);
@@ -964,6 +952,34 @@ int b200adsb_events_import_packed_dev(b200adsb_ctx *c, const uint64_t *d_gathere
     events_import_packed_kernel<<<16, 256, 0, c->stream>>>(
         (const unsigned long long *)d_gathered, (uint32_t)n_ranks, (uint32_t)rows_per_rank, (uint32_t)skip_rank,
         c->d_ev_keys, c->d_ev_ord, c->d_ev_used, kEvSlots - 1, c->d_counters);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+int b200adsb_frames_pack_dev(b200adsb_ctx *c, const b200adsb_frame *d_frames, const uint32_t *d_count,
+                             size_t count, b200adsb_frame *d_block, size_t rows_cap)
+{
+    if (!c || !d_block || rows_cap == 0 || rows_cap > 0xfffffffeu || (!d_frames && (d_count || count)))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    frames_pack_kernel<<<8, 256, 0, c->stream>>>(d_frames, d_count, (uint32_t)std::min<size_t>(count, 0xffffffffu),
+                                                  d_block, (uint32_t)rows_cap);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+int b200adsb_frames_merge_dev(b200adsb_ctx *c, const b200adsb_frame *d_gathered, size_t n_ranks,
+                              size_t rows_cap, b200adsb_frame *d_out, size_t cap, uint32_t *d_n_out)
+{
+    if (!c || !d_gathered || !d_n_out || n_ranks == 0 || rows_cap == 0 || rows_cap > 0xfffffffeu || (!d_out && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    frames_merge_kernel<<<16, 256, 0, c->stream>>>(d_gathered, (uint32_t)n_ranks, (uint32_t)rows_cap, d_out,
+                                                   (uint32_t)std::min<size_t>(cap, 0xffffffffu), d_n_out);
     CK(c, cudaGetLastError());
     c->timing.other_launches++;
     return B200ADSB_OK;

@@ -72,7 +72,6 @@ struct ScanParams {
     unsigned long long stride; // IQ: samples between buffers; MAG: u16 elements
     int T, tiles_per_buffer;
     int vec_ok;                // 16-byte aligned base and stride % 4 == 0
-    uint32_t pf_dist;          // blocks resident at once on the device (L2 prefetch distance in tiles); 0: off
     uint32_t *rec;             // pool of 6-word records {j, w[5]}
     uint32_t pool_cap;
     uint2 *tile_dir;           // per tile of the batch: (pool base, count)
@@ -82,8 +81,7 @@ struct ScanParams {
     uint32_t *ev_used;
     uint32_t ev_mask;
     unsigned long long ord_first, ord_stride;
-    const uint32_t *crc_tabs;  // CRC-24 field tables (global memory, L1 resident)
-    const uint32_t *crc_lanes; // [kLaneTabs][32]: the same as per-lane shuffle tables (a112_sh / a56_sh)
+    const uint32_t *crc_lanes; // [kLaneTabs][32]: CRC-24 field tables, one entry per lane (a112_sh / a56_sh)
     const uint32_t *lut;       // [12][5][5] field extraction table for this tile size
     // opt-in stream continuity (B200ADSB_OPT_CARRY): the 326 leading MagnitudeBuffer slots of a
     // buffer hold the previous buffer's last samples instead of zeros
@@ -245,36 +243,11 @@ __device__ __forceinline__ uint32_t mulx(uint32_t s)
     s <<= 1;
     return (s & 0x1000000u) ? (s ^ 0x1FFF409u) : s;
 }
-__device__ __forceinline__ uint32_t a112(const uint32_t *t, uint32_t f)
-{
-    return __ldg(t + (f & 0xff)) ^ __ldg(t + 256 + ((f >> 8) & 0xff)) ^ __ldg(t + 512 + ((f >> 16) & 0x3f));
-}
-__device__ __forceinline__ uint32_t a56(const uint32_t *t, uint32_t f)
-{
-    return __ldg(t + kTab56 + (f & 0xff)) ^ __ldg(t + kTab56 + 256 + ((f >> 8) & 7));
-}
-__device__ __forceinline__ uint32_t syn112_fields(const uint32_t *t, const uint32_t f[5])
-{
-    uint32_t s = a112(t, f[0]);
-    s = mulx(s) ^ a112(t, f[1]);
-    s = mulx(s) ^ a112(t, f[2]);
-    s = mulx(s) ^ a112(t, f[3]);
-    s = mulx(s) ^ a112(t, f[4]);
-    return s ^ (((f[0] >> 22) & 1u) << 1) ^ ((f[1] >> 22) & 1u);   // bits 110, 111
-}
-__device__ __forceinline__ uint32_t syn56_fields(const uint32_t *t, const uint32_t f[5])
-{
-    uint32_t s = a56(t, f[0]);
-    s = mulx(s) ^ a56(t, f[1]);
-    s = mulx(s) ^ a56(t, f[2]);
-    s = mulx(s) ^ a56(t, f[3]);
-    s = mulx(s) ^ a56(t, f[4]);
-    return s ^ ((f[0] >> 11) & 1u);                                 // bit 55
-}
-// The same field sums with the tables held in registers, one entry per lane, and looked up with warp
-// shuffles (5-bit chunks of the field: shfl takes the lane index modulo 32, so `f >> 5c` needs no mask).
-// A table lookup through L1 costs ~7 tag wavefronts per warp on the LSU pipe, a shuffle one; the LSU pipe is
-// the kernel's busiest unit (profiles/r2).  All 32 lanes must execute these together.
+// Field sums a112(f) = sum_{m<=21} f[m] x^(107-5m), a56(f) = sum_{m<=10} f[m] x^(51-5m) with the tables held
+// in registers, one entry per lane, and looked up with warp shuffles (5-bit chunks of the field: shfl takes
+// the lane index modulo 32, so `f >> 5c` needs no mask).  A table lookup through L1 costs ~7 tag wavefronts
+// per warp on the LSU pipe, a shuffle one, and 70 instead of 103 instructions per long message
+// (profiles/r2).  All 32 lanes must execute these together.
 //   lanes[c][v], c = 0..4: sum_{b<5, 5c+b<=21} v[b] x^(107-5(5c+b))      (long)
 //   lanes[5+c][v], c = 0..1: sum_{b<5} v[b] x^(51-5(5c+b))               (short; m = 10 is x^1 = 2)
 constexpr int kLaneTabs = 7;
@@ -1272,6 +1245,82 @@ __global__ void save_tail_kernel(const uint32_t *in, unsigned long long stride, 
     if (!found && back < kTrailing)
         w = old_tail[kTrailing - 1 - back];
     new_tail[k] = w;
+}
+
+// ================================================================== frame gather (sharded streams)
+// The reference emits ONE stream of frames in (buffer, j) order (dump1090_rs/src/main.rs:166-200).
+// A sharded run leaves every rank with the frames of its own buffers (local buffer indices, ascending
+// (buffer, j)); they travel as fixed-size blocks -- row 0 = {count, 0, ...}, rows 1.. = frames -- through
+// one all-gather, and every rank (or only the emitting one) merges them:
+// frames_pack_kernel: this rank's block.  count: *d_count if given, else `count`.
+__global__ void frames_pack_kernel(const b200adsb_frame *frames, const uint32_t *d_count, uint32_t count,
+                                   b200adsb_frame *block, uint32_t rows_cap)
+{
+    const uint32_t n = d_count ? *d_count : count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        uint32_t *h = reinterpret_cast<uint32_t *>(block);
+        h[0] = n;
+        for (int k = 1; k < 7; k++)
+            h[k] = 0;
+    }
+    const uint32_t m = min(n, rows_cap);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(frames);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(block + 1);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 7u * m; i += gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+__device__ __forceinline__ unsigned long long frame_key(const b200adsb_frame *f, uint32_t rank, uint32_t world)
+{
+    return ((unsigned long long)(f->buffer * world + rank) << 32) | f->j;   // round-robin dealing: g = local * world + rank
+}
+// frames_merge_kernel: n_ranks blocks of (1 + rows_cap) rows -> out[] in global (buffer, j) order with global
+// buffer indices.  A frame's slot = its index in its own list + the number of frames with a smaller key in
+// every other list (binary search; keys of different ranks never tie: they are different buffers).
+// n_out[0] = total frames, n_out[1] = 1 if a rank had more frames than rows_cap or the total exceeds cap.
+__global__ void frames_merge_kernel(const b200adsb_frame *gathered, uint32_t n_ranks, uint32_t rows_cap,
+                                    b200adsb_frame *out, uint32_t cap, uint32_t *n_out)
+{
+    const size_t stride = (size_t)rows_cap + 1;
+    uint32_t total = 0, ovf = 0;
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        const uint32_t c = *reinterpret_cast<const uint32_t *>(gathered + r * stride);
+        ovf |= c > rows_cap ? 1u : 0u;
+        total += min(c, rows_cap);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        n_out[0] = total;
+        n_out[1] = (ovf || total > cap) ? 1u : 0u;
+    }
+    uint32_t base = 0;
+    for (uint32_t r = 0; r < n_ranks; r++) {
+        const b200adsb_frame *mine = gathered + r * stride + 1;
+        const uint32_t cnt = min(*reinterpret_cast<const uint32_t *>(gathered + r * stride), rows_cap);
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) {
+            const unsigned long long key = frame_key(mine + i, r, n_ranks);
+            uint32_t pos = i;
+            for (uint32_t q = 0; q < n_ranks; q++) {
+                if (q == r)
+                    continue;
+                const b200adsb_frame *other = gathered + q * stride + 1;
+                uint32_t lo = 0, hi = min(*reinterpret_cast<const uint32_t *>(gathered + q * stride), rows_cap);
+                while (lo < hi) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (frame_key(other + mid, q, n_ranks) < key)
+                        lo = mid + 1;
+                    else
+                        hi = mid;
+                }
+                pos += lo;
+            }
+            if (pos < cap) {
+                b200adsb_frame f = mine[i];
+                f.buffer = f.buffer * n_ranks + r;
+                out[pos] = f;
+            }
+        }
+        base += cnt;
+    }
+    (void)base;
 }
 
 // ================================================================== filter helpers

@@ -45,33 +45,14 @@ constexpr int k7ListCap = 1024;             // template matches gated per round 
 #define B200_SCAN7_FILL_ALL 1               // 1: all warps fill the candidate list (0: warp 0 alone)
 #endif
 #ifndef B200_SCAN7_RING
-#define B200_SCAN7_RING 3                   // IQ rows in flight per lane (cp.async ring); 0: register prefetch
-#endif
-#ifndef B200_SCAN7_MAG_PAD
-#define B200_SCAN7_MAG_PAD 24               // u16 of padding per 192-sample group of the magnitude array (0: dense layout)
-#endif
-#ifndef B200_SCAN7_CRC_SHFL
-#define B200_SCAN7_CRC_SHFL 1               // 1: CRC-24 field tables in registers, looked up by warp shuffle (0: through L1)
-#endif
-#ifndef B200_SCAN7_PF
-#define B200_SCAN7_PF 1                     // 1: a block asks the TMA engine to bring the IQ of the tile one residency wave ahead into L2
+#define B200_SCAN7_RING 3                   // IQ rows in flight per lane (cp.async ring)
 #endif
 #ifndef B200_SCAN7_STOP
 #define B200_SCAN7_STOP 0                   // measurement builds only: 1 = return after the dense phase, 2 = after the gates
 #endif
-#ifndef B200_SCAN7_LIST_ALIAS
-#define B200_SCAN7_LIST_ALIAS 1             // 1: the match list lives in the edge planes (dead after the template pass)
-#endif
-
-// Magnitude array layout.  A lane stores the four magnitudes of a row with one STS.64; the ten groups a
-// warp works on lie 384 bytes apart, i.e. on the same banks: an 11-way conflict that made this one store
-// 23 % of the kernel's shared-memory wavefronts (profiles/r2).  Each group is therefore followed by
-// k7MagPad u16 (group stride 432 B: at most three lanes per bank pair), and the pad holds a COPY of the
-// next group's first 24 magnitudes, so that a reader's window of <= 24 consecutive magnitudes never has to
-// step over a gap: element i of the tile lives at k7MagPad + i + k7MagPad * (i / 192), and so does i + k for
-// k < 24 when addressed from i's group.  (The front pad takes the copy written for group 0.)
-constexpr int k7MagPad = B200_SCAN7_MAG_PAD;
-constexpr int k7GroupStride = k7Group + k7MagPad;
+#ifndef B200_ABL
+#define B200_ABL 0                          // measurement builds only (with B200_SCAN7_STOP=1): ablations of the dense loop, results are wrong
+#endif                                      //   1 no global loads  2 no neighbour shuffles  4 signs by FADD  16 no magnitude arithmetic  32 no magnitude store
 
 // shared memory plan for tile size T
 struct Scan7Smem {
@@ -80,7 +61,7 @@ struct Scan7Smem {
     __host__ __device__ explicit Scan7Smem(int T)
     {
         NG = (T + kHaloTot + k7Group - 1) / k7Group;
-        mag_len = k7MagPad + NG * k7GroupStride + 32;
+        mag_len = NG * k7Group + 32;
         WP = (NG + 1) / 2 + 1;                        // words per plane row (+1 read by funnel shifts)
         nw = (T + 31) / 32;
         size_t o = (size_t)mag_len * 2;
@@ -97,14 +78,9 @@ struct Scan7Smem {
             const size_t ring_b = (size_t)k7Threads * B200_SCAN7_RING * 16, mask_b = (size_t)12 * WP * 16;
             o += ring_b > mask_b ? ring_b : mask_b;
         }
-#if B200_SCAN7_LIST_ALIAS
-        off_list = off_planes + (size_t)5 * 12 * WP * 4;   // rising + falling planes: 2 * 12 * WP words
+        // the match list lives in the rising + falling planes (2 * 12 * WP words), dead after the template pass
+        off_list = off_planes + (size_t)5 * 12 * WP * 4;
         list_cap = 48 * WP < k7ListCap ? 48 * WP : k7ListCap;
-#else
-        off_list = o;
-        o += (size_t)k7ListCap * 2;
-        list_cap = k7ListCap;
-#endif
         off_cand = o;
         o += (size_t)k7CandCap * 2;
         bytes = (o + 15) & ~(size_t)15;
@@ -155,7 +131,19 @@ __device__ __noinline__ Row row_slow(const ScanParams &p, const uint32_t *b32, c
 
 __device__ __forceinline__ uint32_t sgn_in(float x, uint32_t acc)   // acc = acc << 1 | sign(x)
 {
+#if B200_ABL & 4
+    return __float_as_uint(__fadd_rn(__uint_as_float(acc), x));
+#else
     return __funnelshift_l(__float_as_uint(x), acc, 1);
+#endif
+}
+__device__ __forceinline__ u64x mag_pair_abl(uint32_t wa, uint32_t wb)
+{
+#if B200_ABL & 16
+    return f2_pack(__uint_as_float(0x4B000000u | (wa & 0xffffu)), __uint_as_float(0x4B000000u | (wb & 0xffffu)));
+#else
+    return mag_pair_fast2(wa, wb);
+#endif
 }
 
 // the five PPM correlators of a sample pair on first differences u, v, w
@@ -183,7 +171,7 @@ struct DenseState {
 
 // one slot: row r -> magnitudes to shared memory, 28 sign bits into the accumulators
 __device__ __forceinline__ void dense_slot(DenseState &st, const Row r, bool is_c0, int src_lane, uint16_t *mag_row,
-                                           bool store, bool copy)
+                                           bool store)
 {
     float m0, m1, m2, m3;
     f2_unpack(r.q0, m0, m2);
@@ -191,9 +179,13 @@ __device__ __forceinline__ void dense_slot(DenseState &st, const Row r, bool is_
     // right neighbours m4..m6: lane+1's m0..m2 of this slot, or (c == 2) lane-2's m0..m2 of the
     // previous slot = the row 12 samples further
     const float t0 = is_c0 ? st.pm0 : m0, t1 = is_c0 ? st.pm1 : m1, t2 = is_c0 ? st.pm2 : m2;
+#if B200_ABL & 2
+    const float m4 = t0, m5 = t1, m6 = t2;
+#else
     const float m4 = __shfl_sync(0xffffffffu, t0, src_lane);
     const float m5 = __shfl_sync(0xffffffffu, t1, src_lane);
     const float m6 = __shfl_sync(0xffffffffu, t2, src_lane);
+#endif
     st.pm0 = m0; st.pm1 = m1; st.pm2 = m2;
     // first differences as pairs (d0,d2) (d1,d3) (d2,d4) (d3,d5); only the first comes out of aligned
     // register pairs, the others are cheaper as scalar subtractions written straight into their pair
@@ -210,26 +202,19 @@ __device__ __forceinline__ void dense_slot(DenseState &st, const Row r, bool is_
     f2_unpack(n1, a, b); st.acc[1][5] = sgn_in(a, st.acc[1][5]); st.acc[3][5] = sgn_in(b, st.acc[3][5]);
     corr_pair(p0, p1, p2, st.acc[0], st.acc[2]);
     corr_pair(p1, p2, p3, st.acc[1], st.acc[3]);
-    if (store) {
+    if (store && !(B200_ABL & 32)) {
         const uint2 v = make_uint2(__byte_perm(__float_as_uint(m0), __float_as_uint(m1), 0x5410),
                                    __byte_perm(__float_as_uint(m2), __float_as_uint(m3), 0x5410));
         *reinterpret_cast<uint2 *>(mag_row) = v;
-        if (k7MagPad && copy)        // slots 0 and 1: the group's first 24 magnitudes, again behind the previous group
-            *reinterpret_cast<uint2 *>(mag_row - k7MagPad) = v;
     }
 }
 
-// tile magnitude index -> position in the padded array (see k7MagPad); mi < 8192
-__device__ __forceinline__ int mag_pos(int mi)
-{
-    return k7MagPad ? k7MagPad + mi + k7MagPad * (int)(((uint32_t)mi * 43691u) >> 23) : mi;   // mi / 192
-}
 __device__ __forceinline__ void gate_eval7(const uint16_t *mag, uint32_t *surv, int mi, uint32_t cs, int npos)
 {
     const int jl = mi - kHaloFront;
     if (jl < 0 || jl >= npos)
         return;
-    gate_eval(mag + mag_pos(mi), surv, jl, cs);
+    gate_eval(mag + mi, surv, jl, cs);
 }
 __device__ __noinline__ void gate_eval7_cold(const uint16_t *mag, uint32_t *surv, int mi, uint32_t cs, int npos)
 {
@@ -249,7 +234,7 @@ __device__ __forceinline__ void gate_eval_bf(const uint16_t *mag, uint32_t *surv
     const int jl = mi - kHaloFront;
     if (jl < 0 || jl >= npos)
         return;
-    const uint16_t *pp = mag + mag_pos(mi);
+    const uint16_t *pp = mag + mi;
     const int a = pp[1], h = pp[2], b = pp[3], e = pp[4], n5 = pp[5], n6 = pp[6], n7 = pp[7], n8 = pp[8];
     const int c = pp[9], f = pp[10], g = pp[11], d = pp[12];
     const int bc = b + c, ef = e + f;
@@ -322,7 +307,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     uint32_t *masks = reinterpret_cast<uint32_t *>(smem + P.off_masks);     // P3: [12][nwq] x (match, case planes); the ring is dead
     uint16_t *list = reinterpret_cast<uint16_t *>(smem + P.off_list);
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + P.off_cand);
-    const uint32_t *tabs = p.crc_tabs;
     const uint32_t *lut = p.lut;
     __shared__ uint32_t s_base, s_count, s_ok, s_nlong, s_nshort;
 #if B200_SCAN7_FILL_ALL
@@ -342,25 +326,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     }
     const int npos = min(p.T, len - tile_start);
     const int NG = (npos + kHaloTot + k7Group - 1) / k7Group;   // groups actually needed
-#if B200_SCAN7_PF
-    // DRAM -> L2 for the tile that takes this block's place one residency wave later (cp.async.bulk.prefetch.L2:
-    // one instruction, no registers or shared memory held): that block's row loads then hit L2
-    if (!FROM_MAG && tid == 0 && p.vec_ok && p.pf_dist) {
-        const uint32_t t2 = blockIdx.x + p.pf_dist;
-        if (t2 < p.n_buffers * (uint32_t)p.tiles_per_buffer) {
-            const uint32_t tg = p.b0 * (uint32_t)p.tiles_per_buffer + t2;
-            const uint32_t b2 = tg / (uint32_t)p.tiles_per_buffer;
-            const int kt2 = (int)(tg - b2 * (uint32_t)p.tiles_per_buffer);
-            const int len2 = p.lengths ? (int)min(p.lengths[b2], p.spb) : (int)p.spb;
-            const int lo = max(kt2 * p.T - (kTrailing + kHaloFront), 0);
-            const int hi = min(kt2 * p.T - (kTrailing + kHaloFront) + p.T + kHaloTot + 8, len2) & ~3;
-            if (hi > lo) {
-                const uint32_t *src = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b2 * p.stride + lo;
-                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"((uint32_t)(hi - lo) * 4u) : "memory");
-            }
-        }
-    }
-#endif
     const int WP = P.WP;
     const int nwq = (NG + 1) / 2;                                // plane words that carry data
 
@@ -415,9 +380,8 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 f2_unpack(rbnd.q1, st.pm1, y);
                 (void)x;
             }
-            uint16_t *mrow = mag + k7MagPad + k7GroupStride * G + 4 * c + 12 * (k7Slots - 1);
+            uint16_t *mrow = mag + r0 + 12 * (k7Slots - 1);
             if (fast) {
-#if B200_SCAN7_RING > 0
                 // rows travel global -> shared with cp.async (no registers held while in flight): the lane's
                 // private ring keeps B200_SCAN7_RING rows ahead of the one being processed
                 const char *gsrc = reinterpret_cast<const char *>(b32 + s0 + r0) + 48 * (k7Slots - 1);
@@ -425,8 +389,10 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 constexpr uint32_t kRingStride = 16u * k7Threads;
 #pragma unroll
                 for (int d = 0; d < B200_SCAN7_RING; d++) {
+#if !(B200_ABL & 1)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + d * kRingStride),
                                  "l"(gsrc - 48 * d));
+#endif
                     asm volatile("cp.async.commit_group;");
                 }
                 gsrc -= 48 * B200_SCAN7_RING;
@@ -436,43 +402,27 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                     asm volatile("cp.async.wait_group %0;" ::"n"(B200_SCAN7_RING - 1));
                     uint32_t x, y, z, ww;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x), "=r"(y), "=r"(z), "=r"(ww) : "r"(rp));
+#if !(B200_ABL & 1)
                     if (k >= B200_SCAN7_RING)
                         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(rp), "l"(gsrc));
+#endif
                     asm volatile("cp.async.commit_group;");
                     gsrc -= 48;
                     rp += kRingStride;
                     if (rp == ring0 + B200_SCAN7_RING * kRingStride)
                         rp = ring0;
                     Row r;
-                    r.q0 = mag_pair_fast2(x, z);
-                    r.q1 = mag_pair_fast2(y, ww);
-                    dense_slot(st, r, is_c0, src_lane, mrow, own, k < 2);
+                    r.q0 = mag_pair_abl(x, z);
+                    r.q1 = mag_pair_abl(y, ww);
+                    dense_slot(st, r, is_c0, src_lane, mrow, own);
                     mrow -= 12;
                 }
-#else
-                // plain LDG.128 with one row of register prefetch, one slot per iteration
-                const int4 *src = reinterpret_cast<const int4 *>(b32 + s0 + r0) + 3 * (k7Slots - 1);
-                int4 v = __ldg(src);
-#pragma unroll 1
-                for (int k = k7Slots - 1; k >= 0; k--) {
-                    src -= 3;
-                    int4 nv = v;
-                    if (k > 0)
-                        nv = __ldg(src);
-                    Row r;
-                    r.q0 = mag_pair_fast2((uint32_t)v.x, (uint32_t)v.z);
-                    r.q1 = mag_pair_fast2((uint32_t)v.y, (uint32_t)v.w);
-                    dense_slot(st, r, is_c0, src_lane, mrow, own, k < 2);
-                    mrow -= 12;
-                    v = nv;
-                }
-#endif
             } else {
 #pragma unroll 1
                 for (int k = k7Slots - 1; k >= 0; k--) {
                     const int rr = r0 + 12 * k;
                     const Row r = row_slow<FROM_MAG>(p, b32, d16, s0 + rr, i0 + rr, len, cs, b);
-                    dense_slot(st, r, is_c0, src_lane, mrow, own, k < 2);
+                    dense_slot(st, r, is_c0, src_lane, mrow, own);
                     mrow -= 12;
                 }
             }
@@ -651,12 +601,10 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
 
     // ---- P4b: five try-phases per survivor, in windows of k7CandCap survivors (as v6)
     const int C = (int)s_count;
-#if B200_SCAN7_CRC_SHFL
-    CrcLanes crcl;
+    CrcLanes crcl;      // CRC-24 field tables, one entry per lane (looked up by warp shuffle)
 #pragma unroll
     for (int c = 0; c < kLaneTabs; c++)
         crcl.t[c] = __ldg(p.crc_lanes + 32 * c + lane);
-#endif
     const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
     for (int win = 0; win < C; win += k7CandCap) {
 #if B200_SCAN7_FILL_ALL
@@ -749,7 +697,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             }
         }
         __syncthreads();
-#if B200_SCAN7_CRC_SHFL
         {
             // long items, then short ones: each loop has a warp-uniform trip count, so the table shuffles
             // inside are executed by whole warps (lanes past the end carry zeros)
@@ -808,45 +755,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 }
             }
         }
-#else
-        {
-            const int nl = (int)s_nlong, ns = (int)s_nshort;
-            for (int g = tid; g < nl + ns; g += k7Threads) {
-                const bool is_long = g < nl;
-                const uint32_t slot = is_long ? (uint32_t)g : (uint32_t)(k7FieldItems - 1 - (g - nl));
-                const uint32_t *o = fb + 5 * slot;
-                uint32_t f[5] = {o[0], o[1], o[2], o[3], o[4]};
-                const int item = (int)((f[2] >> 22) | ((f[3] >> 22) << 10));
-                f[2] &= 0x3fffffu;
-                f[3] &= 0x3fffffu;
-                const uint32_t df = df_of_fields(f);
-                uint32_t wd;
-                if (is_long) {
-                    const uint32_t syn = syn112_fields(tabs, f);
-                    if (df == 17 || df == 18)          // mode_s/mod.rs:91-109
-                        wd = syn ? 0u : (((df == 17 ? K_DF17 : K_DF18) << 29) | msg_bits<8, 24>(f));
-                    else                                // :110-134
-                        wd = (K_PAR_LONG << 29) | syn;
-                } else {
-                    const uint32_t syn = syn56_fields(tabs, f);
-                    if (df == 11)                       // :73-90
-                        wd = (syn & 0xffff80u) ? 0u
-                                               : ((((syn & 0x7f) ? K_DF11_IID : K_DF11_IID0) << 29) | msg_bits<8, 24>(f));
-                    else                                // :56-72
-                        wd = (K_PAR_SHORT << 29) | syn;
-                }
-                const int ci = item / 5, tt = item - 5 * ci;
-                rec_w[6 * ci + 1 + tt] = wd;
-                const uint32_t kind = wd >> 29;
-                if (kind == K_DF11_IID0 || kind == K_DF17 || kind == K_DF18) {
-                    const uint32_t key = (wd & 0xffffffu) | (kind == K_DF18 ? B200ADSB_ICAO_FILTER_ADSB_NT : 0u);
-                    const uint32_t j = (uint32_t)(tile_start + cand[ci]);
-                    event_add(p.ev_keys, p.ev_ord, p.ev_used, p.ev_mask, p.counters, key,
-                              ord_buf | ((unsigned long long)j << 3) | (unsigned long long)tt);
-                }
-            }
-        }
-#endif
         if (win + k7CandCap >= C)
             break;                       // last window: nothing left to synchronise with
         __syncthreads();

@@ -53,34 +53,66 @@ def exchange_events(pairs, count: int, group=None):
 
 
 class ShardedDemodulator:
-    """This rank's share of a sharded stream: scan -> exchange -> resolve on its Context.
+    """This rank's share of a sharded stream: scan -> exchange -> resolve on its Context, then
+    (optionally) the frame gather that turns the ranks' outputs into the reference's single ordered
+    stream (dump1090_rs/src/main.rs:166-200).
 
-    The exchange is one fixed-size all-gather on the context's stream with no host round trip:
-    row 0 of each rank's block carries its event count (b200adsb_events_pack_dev /
-    b200adsb_events_import_packed_dev)."""
+    The exchanges are fixed-size all-gathers on the context's stream with no host round trip: row 0 of
+    each rank's event block carries its event count and its bad-batch flags
+    (b200adsb_events_pack_dev / b200adsb_events_import_packed_dev), row 0 of its frame block the frame
+    count (b200adsb_frames_pack_dev / b200adsb_frames_merge_dev).  A batch that fails on one rank
+    (candidate pool, event table or exchange buffer overflow) fails on every rank and is committed on
+    none, so the ranks' filters stay identical and every rank takes the same path through the
+    collectives."""
 
-    def __init__(self, ctx, rank: int, world: int, group=None, event_rows: int = 4096):
+    FRAME_BYTES = 28
+
+    def __init__(self, ctx, rank: int, world: int, group=None, event_rows: int = 4096, frame_rows: int = 2048):
         import torch
 
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
-        self.event_rows = event_rows
+        self.event_rows, self.frame_rows = event_rows, frame_rows
         dev = torch.device("cuda", ctx.device)
         self.rows = torch.zeros((event_rows, 2), dtype=torch.int64, device=dev)
         self.gathered = torch.zeros((world * event_rows, 2), dtype=torch.int64, device=dev)
+        self.fblock = torch.zeros(((frame_rows + 1) * self.FRAME_BYTES,), dtype=torch.uint8, device=dev)
+        self.fgathered = torch.zeros((world * (frame_rows + 1) * self.FRAME_BYTES,), dtype=torch.uint8, device=dev)
+        self.n_out = torch.zeros((2,), dtype=torch.int32, device=dev)
         self.position = 0          # stream position (in global buffers) of the next batch
+
+    def _exchange_events(self, poisoned: bool = False) -> None:
+        import torch.distributed as dist
+
+        if self.world <= 1:
+            return
+        if poisoned:
+            # this rank's scan failed before the exchange: still take part in the collective, with a block
+            # that makes every other rank fail the batch too (count beyond the block, EV_OVF flag)
+            self.rows.zero_()
+            self.rows[0, 0] = 1 << 40
+            self.rows[0, 1] = 2
+        else:
+            self.ctx.events_pack_dev(self.rows.data_ptr(), self.event_rows)
+        dist.all_gather_into_tensor(self.gathered, self.rows, group=self.group)
+        if not poisoned:
+            self.ctx.events_import_packed_dev(self.gathered.data_ptr(), self.world, self.event_rows, self.rank)
 
     def step(self, iq_ptr: int, n_local: int, spb: int, stride: int, out_ptr: int, cap: int,
              n_total: int | None = None, counts_ptr: int = 0) -> int:
         """Demodulates this rank's n_local buffers of a batch of n_total stream buffers
-        (default n_local * world); frames (with local buffer indices) go to out_ptr."""
-        import torch.distributed as dist
+        (default n_local * world); frames (with local buffer indices) go to out_ptr.
+        Raises B200AdsbError on EVERY rank when the batch failed on any of them."""
+        from ._ffi import B200AdsbError
 
         n_total = n_local * self.world if n_total is None else n_total
-        self.ctx.scan_batch_dev(iq_ptr, n_local, spb, stride, self.position + self.rank, self.world)
-        if self.world > 1:
-            self.ctx.events_pack_dev(self.rows.data_ptr(), self.event_rows)
-            dist.all_gather_into_tensor(self.gathered, self.rows, group=self.group)
-            self.ctx.events_import_packed_dev(self.gathered.data_ptr(), self.world, self.event_rows, self.rank)
+        err = None
+        try:
+            self.ctx.scan_batch_dev(iq_ptr, n_local, spb, stride, self.position + self.rank, self.world)
+        except B200AdsbError as e:      # (the failed scan has already ended its pending batch)
+            err = e
+        self._exchange_events(poisoned=err is not None)
+        if err is not None:
+            raise err
         n = self.ctx.resolve_batch_dev(out_ptr, cap, counts_ptr)
         self.position += n_total
         return n
@@ -89,15 +121,27 @@ class ShardedDemodulator:
                    result_ptr: int, n_total: int | None = None) -> None:
         """Enqueue-only step: scan, event exchange and resolve are queued on the context's stream
         (which must be torch's current stream, so that the NCCL all-gather is ordered with them);
-        the outcome {frames, overflow flags, candidates, frames > cap} lands in result_ptr
-        (4 x uint32 on the device).  Batches execute in call order."""
-        import torch.distributed as dist
-
+        the outcome {frames, failure flags, candidates, frames > cap} lands in result_ptr
+        (4 x uint32 on the device; flags as documented for b200adsb_demod_iq_batch_dev_async --
+        identical zero / non-zero on every rank).  Batches execute in call order."""
         n_total = n_local * self.world if n_total is None else n_total
         self.ctx.scan_batch_dev_async(iq_ptr, n_local, spb, stride, self.position + self.rank, self.world)
-        if self.world > 1:
-            self.ctx.events_pack_dev(self.rows.data_ptr(), self.event_rows)
-            dist.all_gather_into_tensor(self.gathered, self.rows, group=self.group)
-            self.ctx.events_import_packed_dev(self.gathered.data_ptr(), self.world, self.event_rows, self.rank)
+        self._exchange_events()
         self.ctx.resolve_batch_dev_async(out_ptr, cap, result_ptr)
         self.position += n_total
+
+    def gather_frames(self, frames_ptr: int, out_ptr: int, cap: int, count: int = 0, result_ptr: int = 0):
+        """The ranks' frames of the last step -> the single stream in (global buffer, j) order with global
+        buffer indices, on EVERY rank (any of them can be the emitting one), enqueue-only.  count: frames
+        this rank holds (synchronous step) or result_ptr: the step_async outcome (its word 0 is the count).
+        Returns the device tensor n_out = [frames, overflow] to read after a stream sync."""
+        import torch.distributed as dist
+
+        self.ctx.frames_pack_dev(frames_ptr, self.fblock.data_ptr(), self.frame_rows, count=count, count_ptr=result_ptr)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.fgathered, self.fblock, group=self.group)
+            src = self.fgathered
+        else:
+            src = self.fblock
+        self.ctx.frames_merge_dev(src.data_ptr(), self.world, self.frame_rows, out_ptr, cap, self.n_out.data_ptr())
+        return self.n_out

@@ -192,6 +192,17 @@ int b200adsb_events_import_packed_dev(b200adsb_ctx *ctx, const uint64_t *d_gathe
 int b200adsb_resolve_batch_dev(b200adsb_ctx *ctx, b200adsb_frame *d_out, size_t cap,
                                size_t *n_out, uint32_t *d_per_buffer_counts);
 
+/* frames: the reference emits ONE stream in (buffer, j) order (dump1090_rs/src/main.rs:166-200).  Each
+ * rank packs its frames (local buffer indices) into a fixed-size block of 1 + rows_cap rows of
+ * sizeof(b200adsb_frame): row 0 = {u32 count, 0...}; the blocks are all-gathered; merge writes the single
+ * ordered stream with GLOBAL buffer indices (round robin: global = local * n_ranks + rank) to d_out and
+ * d_n_out[0] = frames, d_n_out[1] = 1 if a rank had more than rows_cap frames or the total exceeds cap.
+ * count: *d_count (device) if d_count != NULL, else `count`.  Enqueue-only, on the context's stream. */
+int b200adsb_frames_pack_dev(b200adsb_ctx *ctx, const b200adsb_frame *d_frames, const uint32_t *d_count,
+                             size_t count, b200adsb_frame *d_block, size_t rows_cap);
+int b200adsb_frames_merge_dev(b200adsb_ctx *ctx, const b200adsb_frame *d_gathered, size_t n_ranks,
+                              size_t rows_cap, b200adsb_frame *d_out, size_t cap, uint32_t *d_n_out);
+
 /* enqueue-only forms (no host round trip; outcome in d_result as for
  * b200adsb_demod_iq_batch_dev_async): scan_async -> events_pack -> all-gather ->
  * events_import_packed -> resolve_async, all on the context's stream */
@@ -250,7 +261,8 @@ int b200adsb_debug_mag_sweep(b200adsb_ctx *ctx, uint64_t *mismatches, uint32_t *
  * src/mode_s/mod.rs:34-139; kinds as in oracle/dump1090_oracle.h). */
 int b200adsb_debug_records(b200adsb_ctx *ctx, uint32_t *buffers, uint32_t *rec6, size_t cap, size_t *n);
 
-/* test hook, pure host: the 840-word CRC-24 field tables used by the scan kernel
+/* test hook, pure host: the 840-word CRC-24 field tables (8/8/6- and 8/3-bit chunks; the scan kernel uses the
+ * 5-bit chunking below)
  * followed by the 256-entry byte table (src/crc.rs:3-260); returns 840. */
 int b200adsb_debug_crc_tabs(uint32_t *out);
 /* the same field sums as 7 tables of 32 entries for warp-shuffle lookup (5-bit chunks); returns 224 */

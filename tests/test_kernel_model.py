@@ -147,27 +147,6 @@ def test_crc_lane_tables(oracle_mod):
         assert s == oracle_mod.modes_checksum(m[:7], 56)
 
 
-def test_padded_magnitude_layout():
-    """scan7.cuh mag_pos: element i of a tile lives at 24 + i + 24*(i/192) (i/192 by multiply-shift), each
-    192-sample group is followed by a copy of the next group's first 24 elements, so a window of up to 24
-    consecutive elements addressed from its first element's group reads the right values."""
-    pad, grp = 24, 192
-    n = 8192
-    for i in range(n):
-        assert (i * 43691) >> 23 == i // grp
-    NG = 40
-    vals = np.arange(NG * grp, dtype=np.int64) + 1000
-    arr = np.full(pad + NG * (grp + pad) + 32, -1, dtype=np.int64)
-    for i in range(NG * grp):                        # what the dense phase stores
-        pos = pad + i + pad * (i // grp)
-        arr[pos] = vals[i]
-        if i % grp < 24:                             # slots 0 and 1 also write the copy
-            arr[pos - pad] = vals[i]
-    for i in range(NG * grp - 24):
-        base = pad + i + pad * (i // grp)
-        assert (arr[base:base + 24] == vals[i:i + 24]).all(), i
-
-
 def test_abi_exports_match_header():
     """Every function declared in include/b200adsb.h is exported by libb200adsb.so."""
     import os
