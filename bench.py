@@ -5,10 +5,16 @@
   python bench.py --impl reference ...                   (CPU restatement of the reference)
 
 A step = one pass of the hot path (IQ -> frames) over one batch of synthetic 2.4 Msps CS16
-buffers of 131,072 samples (512 KiB).  N=1: BASELINE configs[2] (1000 buffers back to back,
-device resident).  N>1: configs[4] style, the stream dealt round-robin over the ranks
-(1024 buffers per rank = 8192 at N=8; weak scaling), with the ICAO add-event all-gather
-between scan and resolve so that the sharded run equals the single stream.
+buffers of 131,072 samples (512 KiB).  The workload is ONE stream of global buffers 0, 1, 2, ...
+(rtl-like noise, torch generator seed 1090; the first few buffers carry injected DF17 traffic from a
+shared aircraft pool so that parity at any N exercises the cross-rank filter exchange):
+  N = 1   BASELINE configs[2]: 1000 buffers back to back, device resident.
+  N > 1   configs[4] style: the stream dealt round-robin over the ranks, 1000 buffers per GPU (weak
+          scaling, the same per-GPU load as N = 1), ICAO add-event all-gather between scan and resolve,
+          frame gather into the single (buffer, j)-ordered stream inside the timed step.
+Sub-records of the same JSON line: `configs0` (one capture through b200adsb_demod_iq, median latency,
+benches/demod_benchmark.rs:7-12), `configs3` (1/10/100 injected messages per buffer), `strong_8192`
+(configs[4] as written: 8192 buffers in total over the N GPUs), `h2d_ceiling`, `iq_scatter`.
 
 `value`  : device-resident inputs, CUDA-event timed, max over ranks.
 `e2e`    : same batch through the host-buffer C-ABI call (pinned host IQ in, frames out),
@@ -16,7 +22,9 @@ between scan and resolve so that the sharded run equals the single stream.
 `roofline`: scan kernel, 4 algorithmic bytes per sample / CUDA-event kernel time, against
            MEASURED_PEAKS.json hbm_gbs.
 `cpu_baseline`: oracle/ (C restatement; the Rust reference cannot be built here) on one host
-           core over a bounded sample of the same batch; also checks frame parity on it.
+           core over a bounded sample of the same batch.
+`parity_on_sample`: the frames of the first global buffers (all ranks' shares, gathered) against the
+           single-stream oracle, at every N.
 """
 from __future__ import annotations
 
@@ -36,6 +44,11 @@ if REPO not in sys.path:
 SAMPLES = 131072
 METRIC = "iq_msamples_per_s"
 UNIT = "Msamples/s"
+SEED = 1090
+BUFFERS_PER_GPU = 1000          # BASELINE configs[2]
+SIGNAL_PER_RANK = 8             # injected-traffic buffers at the head of the stream, per rank
+SIGNAL_MSGS = 24
+SIGNAL_POOL = 8                 # aircraft addresses shared by all signal buffers (=> cross-rank filter events)
 
 
 def peaks():
@@ -65,9 +78,7 @@ class ClockSampler:
         try:
             import pynvml
             pynvml.nvmlInit()
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
-            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(index))
             self._nv = pynvml
             self.source = "nvml"
         except Exception:
@@ -124,43 +135,144 @@ class ClockSampler:
                 "samples": len(self.sm), "source": self.source}
 
 
+def physical_index(index: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        parts = vis.split(",")
+        if index < len(parts) and parts[index].strip().isdigit():
+            return int(parts[index])
+    return index
+
+
+def bind_to_gpu_numa(index: int) -> dict:
+    """Pin this process to the CPUs next to its GPU BEFORE any pinned allocation: cudaHostAlloc pages land on
+    the caller's NUMA node, and a rank whose staging buffers sit on the far socket copies at a fraction of
+    the PCIe rate (round 1: per-GPU H2D fell from 54 to 23 GB/s at N = 8)."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(physical_index(index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        dev = f"/sys/bus/pci/devices/{dom[-4:].lower()}:{rest.lower()}"
+        with open(dev + "/local_cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        try:
+            with open(dev + "/numa_node") as f:
+                info["numa_node"] = int(f.read().strip())
+        except Exception:
+            pass
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info.update(bound=True, cpus=len(cpus))
+    except Exception as e:          # best effort: the bench still runs unbound
+        info["error"] = str(e)[:80]
+    return info
+
+
+def stream_noise(n_global: int, take, device, chunk: int = 64):
+    """Global buffers 0..n_global-1 of the bench stream (rtl-like noise, one torch generator seeded SEED, chunks
+    of 64 global buffers); returns the buffers `take` selects (a list of global indices, ascending) as one
+    int16 tensor [len(take), SAMPLES, 2] on `device`.  Every rank and the reference arm call this with the
+    same n_global-independent prefix property: buffer g does not depend on how many buffers follow it."""
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(SEED)
+    want = list(take)
+    out = torch.empty((len(want), SAMPLES, 2), dtype=torch.int16, device=device)
+    pos = 0
+    for g0 in range(0, n_global, chunk):
+        f = torch.randn((chunk, SAMPLES, 2), generator=g, device=device, dtype=torch.float32) * 5.5 + 127.4
+        sel = []
+        while pos + len(sel) < len(want) and want[pos + len(sel)] < g0 + chunk:
+            sel.append(want[pos + len(sel)] - g0)
+        if sel:
+            u8 = torch.clamp(torch.round(f[sel]), 0, 255)
+            out[pos:pos + len(sel)] = torch.trunc((u8 - 127.4) / 128.0 * 32767.0).to(torch.int16)
+            pos += len(sel)
+        if pos >= len(want):
+            break
+    return out
+
+
+def signal_buffers(n: int):
+    """The injected-traffic buffers that replace global buffers 0..n-1 (numpy, identical everywhere)."""
+    from dump1090_rs_b200 import synth
+    return synth.make_batch(SEED, n, msgs_per_buffer=SIGNAL_MSGS, icao_pool=SIGNAL_POOL)
+
+
+def frames_to_tuples(raw):
+    """uint8 [n, 28] frame rows -> (buffer, j, phase, score, hex)"""
+    import numpy as np
+    return [(int(r[24:28].view(np.uint32)[0]), int(r[20:24].view(np.uint32)[0]), int(r[15]),
+             int(r[16:18].view(np.int16)[0]), bytes(r[: r[14]]).hex()) for r in raw]
+
+
 def run_reference(args) -> int:
     """--impl reference: the reference's CPU algorithm (oracle port; Rust itself cannot be built
-    in this image) on all host threads, independent streams one per thread."""
+    in this image) on all host threads over THE SAME 1000-buffer batch as the GPU arm at N = 1 (one step =
+    one pass over it, buffers dealt to the threads, each thread a private filter as independent receivers
+    would be); also the 1-thread figure the reference's own bench reports."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     import numpy as np
-    from dump1090_rs_b200 import synth
+    import torch
     from oracle import oracle as O
 
     cores = os.cpu_count() or 1
-    nb = max(cores * 4, 16)
-    passes = 8            # each thread goes over its buffers several times per step: amortises thread start-up
-    batch = synth.make_batch(1090, min(nb, 32))
-    reps = (nb + batch.shape[0] - 1) // batch.shape[0]
-    batch = np.concatenate([batch] * reps)[:nb]
+    nb = args.buffers or BUFFERS_PER_GPU
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    batch = stream_noise(nb, range(nb), dev).cpu().numpy()
+    k = min(SIGNAL_PER_RANK, nb)
+    batch[:k] = signal_buffers(k)
     for _ in range(max(args.warmup, 1)):
-        O.bench(batch, nb, SAMPLES, 1, cores, False)
+        O.bench(batch[: 4 * cores], min(4 * cores, nb), SAMPLES, 1, cores, False)
     t = 0.0
     for _ in range(args.steps):
-        sec, _fr = O.bench(batch, nb, SAMPLES, passes, cores, False)
+        sec, _fr = O.bench(batch, nb, SAMPLES, 1, cores, False)
         t += sec
-    value = nb * passes * SAMPLES * args.steps / t / 1e6
+    value = nb * SAMPLES * args.steps / t / 1e6
+    n1 = min(64, nb)
+    O.bench(batch[:n1], n1, SAMPLES, 1, 1, False)
+    sec1, _ = O.bench(batch[:n1], n1, SAMPLES, 3, 1, False)
+    one = n1 * 3 * SAMPLES / sec1 / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32 (+f32 magnitude)",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": f"synthetic 2.4Msps CS16 rtl-like noise, {nb} x 512KiB buffers x {passes} passes per step "
-                               f"(bounded sample of BASELINE configs[2]), {cores} independent streams"},
+        "config": {"workload": workload_text(nb, 1), "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES,
+                   "host_threads": cores, "data_generated_on": dev},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{nb} buffers x {passes} passes x {args.steps} steps, {cores} threads, C restatement of "
-                                   "to_mag+demodulate2400 (rustc unavailable)"},
+                         "sample": f"the whole {nb}-buffer batch, one pass per step x {args.steps} steps, {cores} threads "
+                                   "(buffers dealt to the threads, private filter each), C restatement of "
+                                   "to_mag+demodulate2400 (rustc unavailable)",
+                         "one_thread_value": one,
+                         "one_thread_sample": f"first {n1} buffers x 3 passes, 1 thread (the shape of benches/demod_benchmark.rs)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
+
+
+def workload_text(nb: int, world: int) -> str:
+    base = (f"synthetic 2.4Msps CS16 stream, rtl-like noise (sigma 5.5 LSB of 8 bit, torch generator seed {SEED}), "
+            f"{nb} x 512KiB buffers per GPU per step; the first {SIGNAL_PER_RANK} buffers per GPU carry {SIGNAL_MSGS} injected DF17 "
+            f"each from a pool of {SIGNAL_POOL} aircraft; ")
+    return base + ("BASELINE configs[2]" if world == 1 else
+                   "configs[4]-style round-robin shards (same per-GPU load as N=1) + ICAO event all-gather + frame gather")
 
 
 def main() -> int:
@@ -169,46 +281,42 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--buffers", type=int, default=0, help="buffers per rank (default 1000 at N=1, 1024 at N>1)")
-    ap.add_argument("--msgs", type=int, default=0, help="injected DF17 per buffer in the first 16 buffers")
-    ap.add_argument("--msgs-all", action="store_true", help="repeat the 16 signal buffers over the whole batch (configs[3])")
+    ap.add_argument("--buffers", type=int, default=0, help=f"buffers per rank (default {BUFFERS_PER_GPU})")
     ap.add_argument("--tile", type=int, default=0)
     ap.add_argument("--sync-steps", action="store_true", help="time the synchronous ABI call (one host round trip per step)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (configs0, configs3, strong_8192, ...)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         return run_reference(args)
 
-    import numpy as np
-    import torch
-    import dump1090_rs_b200 as d
-    from dump1090_rs_b200 import _ffi, sharded, synth
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa(local)
+
+    import numpy as np
+    import torch
+    import dump1090_rs_b200 as d
+    from dump1090_rs_b200 import _ffi, sharded
+
     dist = None
+    torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    else:
-        torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    nb = args.buffers or (1000 if world == 1 else 1024)
+    nb = args.buffers or BUFFERS_PER_GPU
 
     # ---- data: this rank's share of the stream (global buffer g = b*world + rank)
-    iq = synth.noise_batch_torch(1090 + rank, nb, device=dev)
-    if args.msgs:
-        k = min(16, nb)
-        inj = synth.make_batch(1090, k, msgs_per_buffer=args.msgs, first_index=rank * 1000)
-        iq[:k] = torch.from_numpy(inj).to(dev)
-        if args.msgs_all:
-            for b0 in range(k, nb, k):
-                iq[b0:b0 + k] = iq[:min(k, nb - b0)]
+    n_sig = min(SIGNAL_PER_RANK, nb) * world
+    iq = stream_noise(nb * world, range(rank, nb * world, world), dev)
+    sig = signal_buffers(n_sig)
+    iq[: n_sig // world] = torch.from_numpy(np.ascontiguousarray(sig[rank::world])).to(dev)
+
     # a real (non-default) stream shared by torch and the library: the timing events below are
     # recorded on the stream the kernels are launched on
     stream = torch.cuda.Stream(device=dev)
@@ -219,55 +327,54 @@ def main() -> int:
         ctx.set_option(_ffi.OPT_TILE, args.tile)
     cap = 1 << 16
     frames = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
+    merged = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
     n_frames = [0]
+    sh = sharded.ShardedDemodulator(ctx, rank, world, frame_rows=4096)
 
-    sh = sharded.ShardedDemodulator(ctx, rank, world) if world > 1 else None
-
-    # N = 1: the timed steps are queued back to back with the enqueue-only entry point
-    # (b200adsb_demod_iq_batch_dev_async): the batch outcome {frames, overflow flags, ...} stays on
-    # the device and is checked after the timed region; warm-up steps use the synchronous call
-    # (which also sizes the candidate pool).  --sync-steps times the synchronous call instead.
+    # The timed steps are queued back to back with the enqueue-only entry points: the batch outcome {frames,
+    # failure flags, ...} stays on the device and is checked after the timed region; warm-up steps use the
+    # synchronous call (which also sizes the candidate pool).  --sync-steps times the synchronous calls instead.
     results = torch.zeros((max(args.steps, 1), 4), dtype=torch.int32, device=dev)
     step_no = [0]
     use_async = [False]
 
-    def step_device():
+    def run_step(iq_t, nbuf, queued):
         ctx.icao_flush()
-        if world == 1 and use_async[0]:
-            ctx.demod_iq_batch_async_ptr(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap,
-                                         results[step_no[0] % results.shape[0]].data_ptr())
+        if world == 1 and queued:
+            r = results[step_no[0] % results.shape[0]]
+            ctx.demod_iq_batch_async_ptr(iq_t.data_ptr(), nbuf, SAMPLES, SAMPLES, frames.data_ptr(), cap, r.data_ptr())
             step_no[0] += 1
         elif world == 1:
-            n_frames[0] = ctx.demod_iq_batch_ptr(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap)
-        elif use_async[0]:
+            n_frames[0] = ctx.demod_iq_batch_ptr(iq_t.data_ptr(), nbuf, SAMPLES, SAMPLES, frames.data_ptr(), cap)
+        elif queued:
+            # scan -> all-gather of ICAO add-events (NCCL) -> resolve -> all-gather of frames -> ordered stream
             sh.position = 0
-            sh.step_async(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap,
-                          results[step_no[0] % results.shape[0]].data_ptr())
+            r = results[step_no[0] % results.shape[0]]
+            sh.step_async(iq_t.data_ptr(), nbuf, SAMPLES, SAMPLES, frames.data_ptr(), cap, r.data_ptr())
+            sh.gather_frames(frames.data_ptr(), merged.data_ptr(), cap, result_ptr=r.data_ptr())
             step_no[0] += 1
         else:
-            # scan -> all-gather of ICAO add-events (NCCL) -> resolve
             sh.position = 0
-            n_frames[0] = sh.step(iq.data_ptr(), nb, SAMPLES, SAMPLES, frames.data_ptr(), cap)
+            n_frames[0] = sh.step(iq_t.data_ptr(), nbuf, SAMPLES, SAMPLES, frames.data_ptr(), cap)
+            sh.gather_frames(frames.data_ptr(), merged.data_ptr(), cap, count=n_frames[0])
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
-    ctx.timing(reset=True)
-    def timed_region(queued: bool):
-        use_async[0] = queued
+    def timed_region(iq_t, nbuf, steps, queued, sample_clocks=True):
         step_no[0] = 0
+        for _ in range(args.warmup):
+            run_step(iq_t, nbuf, False)
+        barrier()
         ctx.timing(reset=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(local) as clk_:
             barrier()
             e0.record()
-            for _ in range(args.steps):
-                step_device()
+            for _ in range(steps):
+                run_step(iq_t, nbuf, queued)
             e1.record()
             barrier()
         ms_ = e0.elapsed_time(e1)
@@ -275,58 +382,83 @@ def main() -> int:
         tim_ = ctx.timing(reset=True)
         ok = True
         if queued:
-            res = results.cpu().numpy()
+            res = results[:min(steps, results.shape[0])].cpu().numpy()
             ok = bool((res[:, 1] == 0).all() and (res[:, 3] == 0).all() and (res[:, 0] == n_frames[0]).all())
             if not ok:
-                print("bench: a queued batch overflowed or disagreed with the synchronous call: %r" % (res.tolist(),),
+                print("bench: a queued batch failed or disagreed with the synchronous call: %r" % (res.tolist(),),
                       file=sys.stderr)
-        use_async[0] = False
+        if dist is not None:   # every rank must take the same path
+            flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            ok = int(flag.item()) == 0
+            t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
         return ms_, tim_, clk_, ok
 
-    queued_steps = not args.sync_steps
-    ms, tim, clk, ok = timed_region(queued_steps)
-    if dist is not None:   # every rank must take the same path
-        flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
-        ok = int(flag.item()) == 0
-    if not ok:             # never report an unverified number: time the synchronous call instead
-        queued_steps = False
-        ms, tim, clk, ok = timed_region(False)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def measure(iq_t, nbuf, steps):
+        """(ms, timing, clocks, queued?) of `steps` steps, queued unless that cannot be verified"""
+        queued = not args.sync_steps
+        ms_, tim_, clk_, ok = timed_region(iq_t, nbuf, steps, queued)
+        if not ok:             # never report an unverified number: time the synchronous call instead
+            queued = False
+            ms_, tim_, clk_, ok = timed_region(iq_t, nbuf, steps, False)
+        return ms_, tim_, clk_, queued
+
+    ms, tim, clk, queued_steps = measure(iq, nb, args.steps)
     total_samples = nb * SAMPLES * world
     value = total_samples * args.steps / (ms * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel (scan): algorithmic bytes = 4 B per IQ sample
-    SCAN_KERNEL = {"6": "scan_kernel<false>"}.get(
-        os.environ.get("B200ADSB_SCAN", "7"), "scan7_kernel<false>")
     peak, peak_src = peaks()
-    # (the scan kernel is launched once per chunk of tiles; sum over the timed region)
-    scan_launches = max(tim["scan_launches"], 1)
-    scan_ms = tim["scan_ms"] / scan_launches
-    alg_bytes = 4.0 * tim["samples"] / scan_launches
-    achieved = 4.0 * tim["samples"] / (tim["scan_ms"] * 1e-3) / 1e9 if tim["scan_ms"] > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
-            tj = json.load(f)
-            traffic = tj.get("dram_bytes_per_sample", None)
-            if traffic is not None:
-                traffic = traffic * tim["samples"] / scan_launches
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if peak else None, "traffic": traffic,
-                "kernel": SCAN_KERNEL, "kernel_ms_per_launch": scan_ms,
-                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
-                "kernel_share_of_step": (tim["scan_ms"] / ms) if ms else None,
-                "kernel_ms_per_step": tim["scan_ms"] / args.steps,
-                "decode_kernel_ms_per_step": tim.get("decode_ms", 0.0) / args.steps,
-                "resolve_kernels_ms_per_step": tim["resolve_ms"] / args.steps}
 
-    # ---- e2e: host-buffer C-ABI call, H2D + D2H inside the timed region
+    def roofline_of(tim_, steps, ms_):
+        launches = max(tim_["scan_launches"], 1)
+        achieved = 4.0 * tim_["samples"] / (tim_["scan_ms"] * 1e-3) / 1e9 if tim_["scan_ms"] > 0 else 0.0
+        traffic = None
+        try:
+            with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+                per = json.load(f).get("dram_bytes_per_sample", None)
+                if per is not None:
+                    traffic = per * tim_["samples"] / launches
+        except Exception:
+            pass
+        return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if peak else None, "traffic": traffic,
+                "kernel": "scan7_kernel<false>", "kernel_ms_per_launch": tim_["scan_ms"] / launches,
+                "algorithmic_bytes_per_launch": 4.0 * tim_["samples"] / launches, "peak_source": peak_src,
+                "kernel_share_of_step": (tim_["scan_ms"] / ms_) if ms_ else None,
+                "kernel_ms_per_step": tim_["scan_ms"] / steps,
+                "resolve_kernels_ms_per_step": tim_["resolve_ms"] / steps}
+
+    roofline = roofline_of(tim, args.steps, ms)
+    launches_main = int(tim["scan_launches"] + tim["other_launches"])
+
+    # ---- parity on the head of the stream, at every N: one synchronous step, frames gathered into the single
+    # ordered stream, the first n_sig global buffers against the sequential oracle
+    run_step(iq, nb, False)
+    ctx.sync()
+    if world > 1:
+        n_out = sh.n_out.cpu().numpy()
+        stream_frames = frames_to_tuples(merged[: int(n_out[0])].cpu().numpy())
+        remote_events = int(sum(int(sh.gathered[r * sh.event_rows, 0].item()) for r in range(world) if r != rank))
+        gather_overflow = int(n_out[1])
+    else:
+        stream_frames = frames_to_tuples(frames[: n_frames[0]].cpu().numpy())
+        remote_events, gather_overflow = 0, 0
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as O
+        o = O.Oracle()
+        ref = []
+        for g in range(n_sig):
+            ref += [(g, f["j"], f["phase"], f["score"], f["msg"].hex()) for f in o.demod_iq(sig[g])]
+        got = [t for t in stream_frames if t[0] < n_sig]
+        parity = {"ok": got == ref and gather_overflow == 0, "global_buffers": n_sig, "frames": len(ref),
+                  "frames_whole_step": len(stream_frames), "events_from_other_ranks": remote_events}
+
+    sub = {}
+    # ---- e2e: host-buffer C-ABI call, H2D + D2H inside the timed region; and the H2D-only ceiling beside it
     e2e = None
     if not args.no_e2e:
         host_iq = torch.empty((nb, SAMPLES, 2), dtype=torch.int16, pin_memory=True)
@@ -339,45 +471,156 @@ def main() -> int:
             nf = ectx.demod_iq_batch_ptr(host_iq.data_ptr(), nb, SAMPLES, SAMPLES, host_frames.data_ptr(), cap, host=True)
         barrier()
         t0 = time.perf_counter()
-        k_e2e = max(3, args.steps // 2)
+        k_e2e = max(3, args.steps // 5)
         for _ in range(k_e2e):
             ectx.icao_flush()
             nf = ectx.demod_iq_batch_ptr(host_iq.data_ptr(), nb, SAMPLES, SAMPLES, host_frames.data_ptr(), cap, host=True)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        # ceiling: the same pinned batch through plain async copies, nothing else
+        stage = torch.empty_like(iq)
+        cs = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(cs):
+            stage.copy_(host_iq, non_blocking=True)
+        cs.synchronize()
+        barrier()
+        t1 = time.perf_counter()
+        with torch.cuda.stream(cs):
+            for _ in range(k_e2e):
+                stage.copy_(host_iq, non_blocking=True)
+        cs.synchronize()
+        dt_copy = time.perf_counter() - t1
         if dist is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            t = torch.tensor([dt, dt_copy], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+            dt, dt_copy = float(t[0].item()), float(t[1].item())
         e2e = {"value": total_samples * k_e2e / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": nb * SAMPLES * 4, "d2h_bytes_per_step": nf * 28 + 64,
                "steps": k_e2e, "frames_per_step": nf}
+        sub["h2d_ceiling"] = {"value": total_samples * k_e2e / dt_copy / 1e6, "unit": UNIT,
+                              "gbytes_per_s_per_gpu": nb * SAMPLES * 4 * k_e2e / dt_copy / 1e9,
+                              "e2e_fraction_of_ceiling": dt_copy / dt, "numa": numa,
+                              "what": "the same pinned host batch through cudaMemcpyAsync alone (max over ranks)"}
         ectx.close()
-        del host_iq
+        del host_iq, stage
 
-    # ---- CPU baseline (rank 0, N=1): oracle on a bounded sample + parity check on it
+    # ---- CPU baseline (rank 0): oracle on a bounded sample of the same batch, one core
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         from oracle import oracle as O
         ns = min(32, nb)
         sample = iq[:ns].cpu().numpy()
-        # parity on the sample (first buffers of the stream; filter state is a prefix property)
-        o = O.Oracle()
-        ref = []
-        for b in range(min(8, ns)):
-            ref += [(b, f["j"], f["phase"], f["score"], f["msg"].hex()) for f in o.demod_iq(sample[b])]
-        raw = frames[: n_frames[0]].cpu().numpy()
-        got = [(int(r[24:28].view(np.uint32)[0]), int(r[20:24].view(np.uint32)[0]), int(r[15]),
-                int(r[16:18].view(np.int16)[0]), bytes(r[: r[14]]).hex()) for r in raw
-               if int(r[24:28].view(np.uint32)[0]) < min(8, ns)]
-        parity = got == ref
         iters = 120          # ~10 s of single-core work
         O.bench(sample, ns, SAMPLES, 1, 1, False)
         sec, _fr = O.bench(sample, ns, SAMPLES, iters, 1, False)
         cpu = {"value": ns * SAMPLES * iters / sec / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"first {ns} buffers of the batch x {iters} passes, 1 thread, C restatement "
+               "sample": f"first {ns} buffers of rank 0's batch x {iters} passes, 1 thread, C restatement "
                          "(oracle/; rustc unavailable so the Rust reference cannot be built)",
-               "host_cpus": os.cpu_count(), "parity_on_sample": parity}
+               "host_cpus": os.cpu_count(), "parity_on_sample": None if parity is None else parity["ok"]}
+
+    if not args.no_sub:
+        # ---- configs[4] as written: 8192 buffers in total over the N GPUs (strong scaling)
+        del iq
+        torch.cuda.empty_cache()
+        nbs = 8192 // world
+        iq_s = stream_noise(nbs * world, range(rank, nbs * world, world), dev)
+        steps_s = max(5, args.steps // 5)
+        ms_s, tim_s, _clk, q_s = measure(iq_s, nbs, steps_s)
+        sub["strong_8192"] = {"value": nbs * world * SAMPLES * steps_s / (ms_s * 1e-3) / 1e6, "unit": UNIT,
+                              "ms_per_step": ms_s / steps_s, "buffers_total": nbs * world, "buffers_per_gpu": nbs,
+                              "steps": steps_s, "queued": q_s, "scaling": "strong",
+                              "roofline_frac": roofline_of(tim_s, steps_s, ms_s)["frac"],
+                              "frames_per_step_this_rank": n_frames[0]}
+        del iq_s
+        torch.cuda.empty_cache()
+
+        if world > 1:
+            # ---- buffer hand-off from one source (K6): rank 0 scatters 64 buffers to every rank over NVLink
+            per = 64
+            recv = torch.empty((per, SAMPLES, 2), dtype=torch.int16, device=dev)
+            src = [torch.empty_like(recv) for _ in range(world)] if rank == 0 else None
+            for _ in range(2):
+                dist.scatter(recv, src, src=0)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            reps = 10
+            for _ in range(reps):
+                dist.scatter(recv, src, src=0)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sc_ms = float(t.item()) / reps
+            out_bytes = (world - 1) * per * SAMPLES * 4
+            sub["iq_scatter"] = {"ms": sc_ms, "gbytes_per_s_out_of_rank0": out_bytes / (sc_ms * 1e-3) / 1e9,
+                                 "nvlink_reference_gbs": 770.0, "frac_of_reference": out_bytes / (sc_ms * 1e-3) / 1e9 / 770.0,
+                                 "msamples_per_s": world * per * SAMPLES / (sc_ms * 1e-3) / 1e6,
+                                 "what": f"torch.distributed.scatter (NCCL) of {per} buffers per rank from rank 0; reference = "
+                                         "measured peer copy 770 GB/s per direction (B200_PROFILING.md)"}
+            del recv, src
+
+        if rank == 0:
+            from dump1090_rs_b200 import synth
+            # ---- configs[3]: injected DF17 at 1 / 10 / 100 per buffer (16 distinct buffers repeated over 256)
+            sub["configs3"] = {}
+            for m in (1, 10, 100):
+                inj = torch.from_numpy(synth.make_batch(SEED, 16, msgs_per_buffer=m)).to(dev)
+                iq_m = inj.repeat(16, 1, 1)
+                c3 = d.Context(local, stream.cuda_stream)
+                c3.set_option(_ffi.OPT_PROFILE, 1)
+                res3 = torch.zeros((10, 4), dtype=torch.int32, device=dev)
+                for _ in range(3):
+                    c3.icao_flush()
+                    nfm = c3.demod_iq_batch_ptr(iq_m.data_ptr(), 256, SAMPLES, SAMPLES, frames.data_ptr(), cap)
+                torch.cuda.synchronize()
+                c3.timing(reset=True)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for k in range(10):
+                    c3.icao_flush()
+                    c3.demod_iq_batch_async_ptr(iq_m.data_ptr(), 256, SAMPLES, SAMPLES, frames.data_ptr(), cap, res3[k].data_ptr())
+                e1.record()
+                torch.cuda.synchronize()
+                c3.sync()
+                t3 = c3.timing(reset=True)
+                r3 = res3.cpu().numpy()
+                ms3 = e0.elapsed_time(e1)
+                sub["configs3"][str(m)] = {
+                    "value": 256 * SAMPLES * 10 / (ms3 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms3 / 10,
+                    "frames_per_step": nfm, "verified": bool((r3[:, 1] == 0).all() and (r3[:, 0] == nfm).all()),
+                    "scan_ms_per_step": t3["scan_ms"] / 10, "resolve_ms_per_step": t3["resolve_ms"] / 10,
+                    "roofline_frac": 4.0 * t3["samples"] / (t3["scan_ms"] * 1e-3) / 1e9 / peak if t3["scan_ms"] else None,
+                    "buffers": 256}
+                c3.close()
+                del iq_m, inj
+            # ---- configs[0]: the cargo bench '01' case, one capture per call (benches/demod_benchmark.rs:7-12,23)
+            try:
+                z = np.load(os.path.join(REPO, "tests", "golden", "captures.npz"))
+                cap_iq = np.ascontiguousarray(z["test_1641427457780"].reshape(-1, 2)[:, ::-1])
+                c0 = d.Context(local)
+                lat = []
+                for k in range(230):
+                    t0 = time.perf_counter()
+                    c0.icao_flush()
+                    fr0 = c0.demod_iq(cap_iq)
+                    if k >= 30:
+                        lat.append(time.perf_counter() - t0)
+                med = statistics.median(lat)
+                rec0 = {"capture": "test_iq/test_1641427457780.iq", "call": "icao_flush + b200adsb_demod_iq (host pointer in, frames out)",
+                        "median_ms": med * 1e3, "p90_ms": sorted(lat)[int(0.9 * len(lat))] * 1e3,
+                        "value": SAMPLES / med / 1e6, "unit": UNIT, "frames": len(fr0), "iterations": len(lat),
+                        "reference_readme_ms": 3.695}
+                if not args.no_cpu:
+                    from oracle import oracle as O
+                    O.bench(cap_iq[None], 1, SAMPLES, 20, 1, True)
+                    sec0, _ = O.bench(cap_iq[None], 1, SAMPLES, 200, 1, True)
+                    rec0["cpu_port_ms"] = sec0 / 200 * 1e3
+                    rec0["speedup_vs_cpu_port_1_thread"] = (sec0 / 200) / med
+                sub["configs0"] = rec0
+                c0.close()
+            except Exception as e:
+                sub["configs0"] = {"error": str(e)[:120]}
 
     if rank == 0:
         line = {
@@ -385,19 +628,21 @@ def main() -> int:
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32 (+f32 magnitude)",
             "data": "synthetic",
-            "config": {"workload": (f"synthetic 2.4Msps CS16 rtl-like noise (sigma 5.5 LSB of 8 bit), {nb} x 512KiB "
-                                    f"buffers per GPU per step, {'BASELINE configs[2]' if world == 1 else 'configs[4] round-robin shards + ICAO event all-gather'}"),
-                       "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES, "injected_msgs": args.msgs, "injected_in_all_buffers": bool(args.msgs_all),
+            "config": {"workload": workload_text(nb, world),
+                       "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES,
                        "l2": f"inputs {nb * SAMPLES * 4 / 2**20:.0f} MiB per GPU > 126 MB L2 (no flush needed)",
-                       "frames_per_step": n_frames[0],
+                       "frames_per_step_rank0": n_frames[0],
                        "step_call": ("synchronous ABI calls (host round trips inside every step)" if not queued_steps else
                                      ("b200adsb_demod_iq_batch_dev_async" if world == 1 else
-                                      "b200adsb_scan_batch_dev_async + events all-gather + b200adsb_resolve_batch_dev_async")
+                                      "b200adsb_scan_batch_dev_async + events all-gather + b200adsb_resolve_batch_dev_async + "
+                                      "frames pack / all-gather / merge")
                                      + " (steps queued back to back, outcomes checked after the timed region)")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(tim["scan_launches"] + tim["other_launches"]),
+            "parity_on_sample": None if parity is None else parity["ok"], "parity": parity,
+            "gpu_launches": launches_main,
             "clocks": clk.summary(),
         }
+        line.update(sub)
         print(json.dumps(line))
     ctx.close()
     if dist is not None:
