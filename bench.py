@@ -253,8 +253,9 @@ def run_reference(args) -> int:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/i32 (+f32 magnitude)",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": workload_text(nb, 1), "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES,
-                   "host_threads": cores, "data_generated_on": dev},
+        "config": {"workload": workload_text(nb, max(args.gpus, 1)), "buffers_per_gpu": nb, "samples_per_buffer": SAMPLES,
+                   "host_threads": cores, "data_generated_on": dev,
+                   "sample": "one GPU's share of the stream per step (rank 0's batch at N = 1): the CPU arm is one host"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"the whole {nb}-buffer batch, one pass per step x {args.steps} steps, {cores} threads "
                                    "(buffers dealt to the threads, private filter each), C restatement of "
@@ -537,7 +538,7 @@ def main() -> int:
         if world > 1:
             # ---- buffer hand-off from one source (K6): rank 0 scatters 64 buffers to every rank over NVLink
             per = 64
-            recv = torch.empty((per, SAMPLES, 2), dtype=torch.int16, device=dev)
+            recv = torch.empty((per, SAMPLES), dtype=torch.int32, device=dev)      # one CS16 pair per word (NCCL has no int16)
             src = [torch.empty_like(recv) for _ in range(world)] if rank == 0 else None
             for _ in range(2):
                 dist.scatter(recv, src, src=0)

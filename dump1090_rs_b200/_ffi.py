@@ -100,6 +100,9 @@ _PROTOS = {
     "b200adsb_demod_iq_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                               C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                               C.c_void_p]),
+    "b200adsb_demod_iq_batch_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "b200adsb_demod_iq_batch_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "b200adsb_scan_batch_dev_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                 C.c_void_p, C.c_uint64, C.c_uint64]),
     "b200adsb_resolve_batch_dev_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

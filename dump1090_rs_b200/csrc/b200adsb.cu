@@ -76,6 +76,19 @@ struct b200adsb_ctx {
     uint32_t *d_lengths = nullptr;
     size_t lengths_cap = 0;
 
+    // receive-loop slots (b200adsb_demod_iq_batch_submit / _wait): device staging, frames, outcome, completion
+    struct Slot {
+        void *d_iq = nullptr;
+        size_t iq_bytes = 0;
+        uint32_t *d_lengths = nullptr;
+        size_t lengths_cap = 0;
+        b200adsb_frame *d_frames = nullptr;
+        size_t frames_cap = 0;
+        uint32_t *d_result = nullptr;
+        cudaEvent_t done = nullptr;
+        bool in_flight = false;
+    } slots[2];
+
     unsigned long long next_ordinal = 0;   // stream position (buffers) for the fused entry points
     Pending cur;
     std::vector<EventPair> scan_events, other_events;
@@ -730,6 +743,13 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
     cudaFree(c->d_cta_sum);
     cudaFree(c->d_bloom);
     cudaFree(c->d_tails);
+    for (auto &sl : c->slots) {
+        cudaFree(sl.d_iq);
+        cudaFree(sl.d_lengths);
+        cudaFree(sl.d_frames);
+        cudaFree(sl.d_result);
+        if (sl.done) cudaEventDestroy(sl.done);
+    }
     cudaFree(c->d_stage);
     cudaFree(c->d_frames);
     cudaFree(c->d_counts);
@@ -1128,6 +1148,68 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers
     if (n_out)
         *n_out = total_frames;
     return status;
+}
+
+// ------------------------------------------------------------------ receive loop (double buffered)
+int b200adsb_demod_iq_batch_submit(b200adsb_ctx *c, int slot, const int16_t *iq, size_t n_buffers, size_t spb,
+                                   size_t stride, const uint32_t *lengths, b200adsb_frame *out, size_t cap,
+                                   uint32_t *result)
+{
+    if (!c || slot < 0 || slot > 1 || (!iq && n_buffers && spb) || (!out && cap) || !result)
+        return B200ADSB_ERR_BAD_ARG;
+    if (spb > (size_t)kMaxSamples || (stride < spb && n_buffers > 1) || n_buffers == 0)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    b200adsb_ctx::Slot &sl = c->slots[slot];
+    if (sl.in_flight)
+        return B200ADSB_ERR_STATE;       // wait for the previous batch of this slot first
+    const size_t dstride = (spb + 3) & ~(size_t)3;
+    rc = grow(c, (unsigned char **)&sl.d_iq, &sl.iq_bytes, std::max<size_t>(n_buffers * dstride * 4, 16), 1);
+    if (rc) return rc;
+    rc = grow(c, &sl.d_frames, &sl.frames_cap, std::max<size_t>(cap, 1));
+    if (rc) return rc;
+    if (!sl.d_result)
+        CK(c, cudaMalloc((void **)&sl.d_result, 16));
+    if (!sl.done)
+        CK(c, cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    int16_t *d_iq = reinterpret_cast<int16_t *>(sl.d_iq);
+    const uint32_t *d_len = nullptr;
+    if (lengths) {
+        rc = grow(c, &sl.d_lengths, &sl.lengths_cap, n_buffers);
+        if (rc) return rc;
+        CK(c, cudaMemcpyAsync(sl.d_lengths, lengths, n_buffers * 4, cudaMemcpyHostToDevice, c->stream));
+        d_len = sl.d_lengths;
+    }
+    if (spb) {
+        if (stride == dstride)
+            CK(c, cudaMemcpyAsync(d_iq, iq, n_buffers * dstride * 4, cudaMemcpyHostToDevice, c->stream));
+        else
+            CK(c, cudaMemcpy2DAsync(d_iq, dstride * 4, iq, stride * 4, spb * 4, n_buffers, cudaMemcpyHostToDevice,
+                                    c->stream));
+    }
+    rc = b200adsb_demod_iq_batch_dev_async(c, d_iq, n_buffers, spb, dstride, d_len, sl.d_frames, cap, sl.d_result);
+    if (rc) return rc;
+    CK(c, cudaMemcpyAsync(result, sl.d_result, 16, cudaMemcpyDeviceToHost, c->stream));
+    if (cap)   // the frame count is only known on the device: the whole (small) array travels
+        CK(c, cudaMemcpyAsync(out, sl.d_frames, cap * sizeof(b200adsb_frame), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaEventRecord(sl.done, c->stream));
+    sl.in_flight = true;
+    return B200ADSB_OK;
+}
+
+int b200adsb_demod_iq_batch_wait(b200adsb_ctx *c, int slot)
+{
+    if (!c || slot < 0 || slot > 1)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    b200adsb_ctx::Slot &sl = c->slots[slot];
+    if (!sl.in_flight)
+        return B200ADSB_ERR_STATE;
+    CK(c, cudaEventSynchronize(sl.done));
+    sl.in_flight = false;
+    return B200ADSB_OK;
 }
 
 int b200adsb_demod_iq(b200adsb_ctx *c, const int16_t *iq, size_t n, b200adsb_frame *out, size_t cap,

@@ -50,6 +50,9 @@ constexpr int k7ListCap = 1024;             // template matches gated per round 
 #ifndef B200_SCAN7_STOP
 #define B200_SCAN7_STOP 0                   // measurement builds only: 1 = return after the dense phase, 2 = after the gates
 #endif
+#ifndef B200_SCAN7_STAGGER
+#define B200_SCAN7_STAGGER 1500             // ns of start delay per residency rank of a first-wave block (0: off)
+#endif
 #ifndef B200_ABL
 #define B200_ABL 0                          // measurement builds only (with B200_SCAN7_STOP=1): ablations of the dense loop, results are wrong
 #endif                                      //   1 no global loads  2 no neighbour shuffles  4 signs by FADD  16 no magnitude arithmetic  32 no magnitude store
@@ -314,6 +317,14 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
 #endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if B200_SCAN7_STAGGER
+    // The blocks of the first residency wave start together and, tiles being equal work, stay in the same
+    // phase for many tiles: all dense (FP pipes contended) or all sparse (latency bound) at once.  A start
+    // offset per residency rank mixes the phases on every SM from the first tile on: +1.5 % at 1000
+    // buffers, +1.8 % at 8192 (profiles/r2).
+    if (blockIdx.x < 148u * B200_SCAN7_MIN_BLOCKS)
+        __nanosleep((blockIdx.x / 148u) * B200_SCAN7_STAGGER);
+#endif
     const uint32_t tile = p.b0 * (uint32_t)p.tiles_per_buffer + blockIdx.x;   // tile of the batch
     const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
     const int kt = (int)(tile - b * (uint32_t)p.tiles_per_buffer);

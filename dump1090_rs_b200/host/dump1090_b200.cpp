@@ -7,6 +7,11 @@
 //          "*{hex};\n" per frame -> stdout unless --quiet, and to every TCP client;
 //          clients that reset their connection are dropped }
 //
+// The reference's demodulation blocks its next `stream.read` (main.rs:161-167).  Here the loop is double
+// buffered: read k+1 fills one pinned buffer while the GPU demodulates read k out of the other
+// (b200adsb_demod_iq_batch_submit / _wait); frames leave in the same order as from the serial loop
+// (--serial keeps that one for comparison).
+//
 // Sources:  --file capture.iq   the reference's capture format (utils.rs:8-40: im, re pairs)
 //           --raw path | -      raw interleaved CS16 (re, im), e.g. a pipe from an SDR tool
 // --batch K collects K reads into one b200adsb_demod_iq_batch call (identical frames, in order).
@@ -28,6 +33,8 @@ struct Options {
     std::string file, raw;
     std::size_t mtu = MODES_MAG_BUF_SAMPLES, batch = 1;
     int wait_clients = 0;               // test aid: do not start before this many clients are connected
+    bool serial = false;                // one synchronous call per read, as the reference's loop
+    std::size_t frame_cap = 1 << 14;    // frame slots per batch
 };
 
 static bool parse(int argc, char **argv, Options &o)
@@ -49,6 +56,8 @@ static bool parse(int argc, char **argv, Options &o)
         else if (a == "--mtu") o.mtu = (std::size_t)std::atoll(val("--mtu"));
         else if (a == "--batch") o.batch = (std::size_t)std::atoll(val("--batch"));
         else if (a == "--wait-clients") o.wait_clients = std::atoi(val("--wait-clients"));
+        else if (a == "--serial") o.serial = true;
+        else if (a == "--frame-cap") o.frame_cap = (std::size_t)std::atoll(val("--frame-cap"));
         else return false;
     }
     return (!o.file.empty() || !o.raw.empty()) && o.mtu >= 1 && o.mtu <= MODES_MAG_BUF_SAMPLES && o.batch >= 1;
@@ -60,7 +69,7 @@ int main(int argc, char **argv)
     if (!parse(argc, argv, opt)) {
         std::fprintf(stderr,
                      "usage: %s (--file capture.iq | --raw path|-) [--host 127.0.0.1] [--port 30002] [--quiet]\n"
-                     "          [--mtu samples<=131072] [--batch reads] [--wait-clients n]\n", argv[0]);
+                     "          [--mtu samples<=131072] [--batch reads] [--wait-clients n] [--serial] [--frame-cap n]\n", argv[0]);
         return 2;
     }
     try {
@@ -92,52 +101,116 @@ int main(int argc, char **argv)
         }
 
         Context &ctx = Context::global();
-        // pinned staging for `batch` reads (the host entry points accept pageable memory too, only slower)
-        Complex16 *buf = static_cast<Complex16 *>(b200adsb_host_alloc(opt.batch * opt.mtu * sizeof(Complex16)));
-        if (!buf)
-            throw std::runtime_error("pinned allocation failed");
-        std::vector<std::uint32_t> lengths(opt.batch);
-        std::vector<b200adsb_frame> frames(1 << 16);
-        std::size_t total = 0;
-        for (bool eof = false; !eof;) {
-            server.accept_one();                               // main.rs:154-157
+        // two pinned staging sets of `batch` reads each (the host entry points accept pageable memory too,
+        // only slower and without overlap)
+        struct Set {
+            Complex16 *buf = nullptr;
+            std::vector<std::uint32_t> lengths;
+            b200adsb_frame *frames = nullptr;
+            std::uint32_t *result = nullptr;
             std::size_t nreads = 0;
-            while (nreads < opt.batch) {
-                const std::size_t len = read(buf + nreads * opt.mtu);
-                if (len == 0) {
-                    eof = true;
-                    break;
-                }
-                lengths[nreads++] = (std::uint32_t)len;
-            }
-            if (nreads == 0)
-                break;
-            std::size_t n = 0;
-            if (nreads == 1)                                   // main.rs:166-167
-                ctx.check(b200adsb_demod_iq(ctx.raw(), reinterpret_cast<const std::int16_t *>(buf), lengths[0],
-                                            frames.data(), frames.size(), &n), "demod_iq");
-            else
-                ctx.check(b200adsb_demod_iq_batch(ctx.raw(), reinterpret_cast<const std::int16_t *>(buf), nreads,
-                                                  opt.mtu, opt.mtu, lengths.data(), frames.data(), frames.size(), &n,
-                                                  nullptr), "demod_iq_batch");
+        } set[2];
+        for (auto &st : set) {
+            st.buf = static_cast<Complex16 *>(b200adsb_host_alloc(opt.batch * opt.mtu * sizeof(Complex16)));
+            st.frames = static_cast<b200adsb_frame *>(b200adsb_host_alloc(opt.frame_cap * sizeof(b200adsb_frame)));
+            st.result = static_cast<std::uint32_t *>(b200adsb_host_alloc(16));
+            st.lengths.resize(opt.batch);
+            if (!st.buf || !st.frames || !st.result)
+                throw std::runtime_error("pinned allocation failed");
+        }
+        std::size_t total = 0;
+        auto emit = [&](const b200adsb_frame *fr, std::size_t n) {
             if (n == 0)
-                continue;                                      // main.rs:170
+                return;                                        // main.rs:170
             std::vector<std::string> lines;
             lines.reserve(n);
             for (std::size_t i = 0; i < n; i++) {              // main.rs:171-181
                 char line[40];
                 std::size_t len = 0;
-                b200adsb_format_avr(&frames[i], 1, line, sizeof line, &len);
+                b200adsb_format_avr(&fr[i], 1, line, sizeof line, &len);
                 lines.emplace_back(line, len);
                 if (!opt.quiet)
                     std::fwrite(line, 1, len, stdout);
             }
             total += n;
             server.broadcast(lines);                           // main.rs:183-199
+        };
+        auto fill = [&](Set &st) -> bool {                     // `batch` reads; false at end of input
+            st.nreads = 0;
+            while (st.nreads < opt.batch) {
+                const std::size_t len = read(st.buf + st.nreads * opt.mtu);
+                if (len == 0)
+                    return false;
+                st.lengths[st.nreads++] = (std::uint32_t)len;
+            }
+            return true;
+        };
+        auto demod_sync = [&](Set &st) {                       // main.rs:166-167, one blocking call
+            std::size_t n = 0;
+            if (st.nreads == 1)
+                ctx.check(b200adsb_demod_iq(ctx.raw(), reinterpret_cast<const std::int16_t *>(st.buf), st.lengths[0],
+                                            st.frames, opt.frame_cap, &n), "demod_iq");
+            else
+                ctx.check(b200adsb_demod_iq_batch(ctx.raw(), reinterpret_cast<const std::int16_t *>(st.buf), st.nreads,
+                                                  opt.mtu, opt.mtu, st.lengths.data(), st.frames, opt.frame_cap, &n,
+                                                  nullptr), "demod_iq_batch");
+            emit(st.frames, n);
+        };
+        if (opt.serial) {
+            for (bool more = true; more;) {
+                server.accept_one();                           // main.rs:154-157
+                more = fill(set[0]);
+                if (set[0].nreads)
+                    demod_sync(set[0]);
+            }
+        } else {
+            // the first call is synchronous (it sizes the candidate pool for this kind of traffic)
+            int cur = 0;
+            bool more = fill(set[cur]);
+            if (set[cur].nreads)
+                demod_sync(set[cur]);
+            bool pending = false;                              // set[cur ^ 1] is on the GPU
+            while (more || pending) {
+                server.accept_one();
+                Set &st = set[cur];
+                st.nreads = 0;
+                if (more)
+                    more = fill(st);                           // overlaps the demodulation of the other set
+                const bool submitted = st.nreads > 0;
+                if (submitted)
+                    ctx.check(b200adsb_demod_iq_batch_submit(ctx.raw(), cur, reinterpret_cast<const std::int16_t *>(st.buf),
+                                                             st.nreads, opt.mtu, opt.mtu, st.lengths.data(), st.frames,
+                                                             opt.frame_cap, st.result), "demod_iq_batch_submit");
+                if (pending) {
+                    Set &pv = set[cur ^ 1];
+                    ctx.check(b200adsb_demod_iq_batch_wait(ctx.raw(), cur ^ 1), "demod_iq_batch_wait");
+                    if (pv.result[1] != 0 || pv.result[3] != 0) {
+                        // the queued batch failed (candidate pool too small for it, or more frames than slots):
+                        // redo it with the blocking call, and the one queued behind it, in order
+                        if (submitted)
+                            ctx.check(b200adsb_demod_iq_batch_wait(ctx.raw(), cur), "demod_iq_batch_wait");
+                        if (pv.result[3] != 0 && pv.result[1] == 0)
+                            throw std::runtime_error("more frames in one batch than --frame-cap");
+                        demod_sync(pv);
+                        if (submitted)
+                            demod_sync(st);
+                        pending = false;
+                        cur ^= 1;
+                        continue;
+                    }
+                    emit(pv.frames, pv.result[0]);
+                }
+                pending = submitted;
+                cur ^= 1;
+            }
         }
         std::fflush(stdout);
         std::fprintf(stderr, "[-] end of input: %zu frames\n", total);
-        b200adsb_host_free(buf);
+        for (auto &st : set) {
+            b200adsb_host_free(st.buf);
+            b200adsb_host_free(st.frames);
+            b200adsb_host_free(st.result);
+        }
         if (rawf && rawf != stdin)
             std::fclose(rawf);
     } catch (const std::exception &e) {

@@ -167,6 +167,18 @@ int b200adsb_demod_iq_batch_dev_async(b200adsb_ctx *ctx, const int16_t *d_iq, si
 
 int b200adsb_async_acknowledge(b200adsb_ctx *ctx);
 
+/* The receive loop, double buffered (main.rs:161-167: `stream.read` -> `to_mag` -> `demodulate2400`, where
+ * the reference's demodulation blocks the next read): submit queues H2D of the host batch (pinned memory
+ * for true asynchrony), the enqueue-only demodulation and the D2H of the 4-word outcome (as d_result above)
+ * and of `cap` frame slots into `out` / `result` (host, pinned), and returns; the caller reads the next
+ * batch from its source while the GPU works, then waits for the slot (0 or 1) and consumes result/out.
+ * A failed batch (result[1] != 0) is redone with b200adsb_demod_iq_batch -- and so is a batch submitted
+ * behind it (its result[1] has bit 3 set), in order. */
+int b200adsb_demod_iq_batch_submit(b200adsb_ctx *ctx, int slot, const int16_t *iq_re_im, size_t n_buffers,
+                                   size_t samples_per_buffer, size_t stride_samples, const uint32_t *lengths,
+                                   b200adsb_frame *out, size_t cap, uint32_t *result);
+int b200adsb_demod_iq_batch_wait(b200adsb_ctx *ctx, int slot);
+
 /* ---- split form for a stream sharded over several GPUs (one context per rank).
  * scan:    stage 1 on this rank's buffers; local buffer b has stream ordinal
  *          first_ordinal + b*ordinal_stride (round robin: first=rank, stride=world).

@@ -89,3 +89,28 @@ def test_receiver_loop_on_raw_pipe(batch, captures, oracle_mod):
     assert len(got) > 0
     assert p.stdout.read() == b""                                         # --quiet
     assert p.returncode == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["double", "serial"])
+def test_receiver_loop_double_buffer_and_recovery(mode, oracle_mod):
+    """The double-buffered loop (read k+1 overlaps the demodulation of read k, main.rs:161-167) emits what
+    the serial loop and the oracle emit -- also when a queued batch overflows the candidate pool (a read
+    that is a dense periodic pattern) and has to be redone together with the batch queued behind it."""
+    from dump1090_rs_b200 import synth
+    n = 131072
+    reads = [synth.make_buffer(55, k, msgs_per_buffer=25, icao_pool=5)[0] for k in range(7)]
+    pat = np.array([3, 8, 11, 4, 11, 1, 4, 9, 8, 1, 11])
+    dense = reads[3].copy()
+    dense[:, 0] = (250 * np.tile(pat, n // len(pat) + 1)[:n] + 100).astype(np.int16)
+    dense[:, 1] = 0
+    reads[3] = dense
+    ref, _ = oracle_stream(oracle_mod, reads)
+    assert len(ref) > 30
+    args = ["--raw", "-", "--quiet", "--frame-cap", "4096"] + (["--serial"] if mode == "serial" else [])
+    p, s = _start_receiver(args)
+    p.stdin.write(np.ascontiguousarray(np.concatenate(reads)).tobytes())
+    p.stdin.close()
+    got = _drain(s, p)
+    assert got == ["*" + f["msg"].hex() + ";" for f in ref]
+    assert p.returncode == 0
