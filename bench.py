@@ -330,7 +330,7 @@ def main() -> int:
     frames = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
     merged = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
     n_frames = [0]
-    sh = sharded.ShardedDemodulator(ctx, rank, world, frame_rows=4096)
+    sh = sharded.ShardedDemodulator(ctx, rank, world, frame_rows=2048)
 
     # The timed steps are queued back to back with the enqueue-only entry points: the batch outcome {frames,
     # failure flags, ...} stays on the device and is checked after the timed region; warm-up steps use the
@@ -439,6 +439,7 @@ def main() -> int:
     # ordered stream, the first n_sig global buffers against the sequential oracle
     run_step(iq, nb, False)
     ctx.sync()
+    sh.fstream.synchronize()
     if world > 1:
         n_out = sh.n_out.cpu().numpy()
         stream_frames = frames_to_tuples(merged[: int(n_out[0])].cpu().numpy())
@@ -636,7 +637,7 @@ def main() -> int:
                        "step_call": ("synchronous ABI calls (host round trips inside every step)" if not queued_steps else
                                      ("b200adsb_demod_iq_batch_dev_async" if world == 1 else
                                       "b200adsb_scan_batch_dev_async + events all-gather + b200adsb_resolve_batch_dev_async + "
-                                      "frames pack / all-gather / merge")
+                                      "frames pack / all-gather / merge on a side stream")
                                      + " (steps queued back to back, outcomes checked after the timed region)")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "parity_on_sample": None if parity is None else parity["ok"], "parity": parity,

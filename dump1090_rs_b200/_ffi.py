@@ -113,9 +113,10 @@ _PROTOS = {
     "b200adsb_events_import_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200adsb_events_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200adsb_events_import_packed_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
-    "b200adsb_frames_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
-    "b200adsb_frames_merge_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
-                                            C.c_void_p]),
+    "b200adsb_frames_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                           C.c_size_t]),
+    "b200adsb_frames_merge_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                            C.c_size_t, C.c_void_p]),
     "b200adsb_resolve_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                              C.c_void_p]),
     "b200adsb_icao_flush": (C.c_int, [C.c_void_p]),

@@ -174,13 +174,15 @@ class Context:
         self._check(self._L.b200adsb_events_import_packed_dev(self._h, gathered_ptr, n_ranks, rows_per_rank,
                                                               skip_rank), "events_import_packed")
 
-    def frames_pack_dev(self, frames_ptr: int, block_ptr: int, rows_cap: int, count: int = 0, count_ptr: int = 0):
-        self._check(self._L.b200adsb_frames_pack_dev(self._h, frames_ptr or None, count_ptr or None, count,
-                                                     block_ptr, rows_cap), "frames_pack")
+    def frames_pack_dev(self, frames_ptr: int, block_ptr: int, rows_cap: int, count: int = 0, count_ptr: int = 0,
+                        stream: int = 0):
+        self._check(self._L.b200adsb_frames_pack_dev(self._h, stream or None, frames_ptr or None, count_ptr or None,
+                                                     count, block_ptr, rows_cap), "frames_pack")
 
-    def frames_merge_dev(self, gathered_ptr: int, n_ranks: int, rows_cap: int, out_ptr: int, cap: int, n_out_ptr: int):
-        self._check(self._L.b200adsb_frames_merge_dev(self._h, gathered_ptr, n_ranks, rows_cap, out_ptr or None, cap,
-                                                      n_out_ptr), "frames_merge")
+    def frames_merge_dev(self, gathered_ptr: int, n_ranks: int, rows_cap: int, out_ptr: int, cap: int, n_out_ptr: int,
+                         stream: int = 0):
+        self._check(self._L.b200adsb_frames_merge_dev(self._h, stream or None, gathered_ptr, n_ranks, rows_cap,
+                                                      out_ptr or None, cap, n_out_ptr), "frames_merge")
 
     def resolve_batch_dev(self, out_ptr: int, cap: int, counts_ptr: int = 0) -> int:
         n = C.c_size_t(0)

@@ -977,28 +977,30 @@ int b200adsb_events_import_packed_dev(b200adsb_ctx *c, const uint64_t *d_gathere
     return B200ADSB_OK;
 }
 
-int b200adsb_frames_pack_dev(b200adsb_ctx *c, const b200adsb_frame *d_frames, const uint32_t *d_count,
+int b200adsb_frames_pack_dev(b200adsb_ctx *c, void *stream, const b200adsb_frame *d_frames, const uint32_t *d_count,
                              size_t count, b200adsb_frame *d_block, size_t rows_cap)
 {
+    cudaStream_t st = stream ? (cudaStream_t)stream : c ? c->stream : nullptr;
     if (!c || !d_block || rows_cap == 0 || rows_cap > 0xfffffffeu || (!d_frames && (d_count || count)))
         return B200ADSB_ERR_BAD_ARG;
     int rc = bind(c);
     if (rc) return rc;
-    frames_pack_kernel<<<8, 256, 0, c->stream>>>(d_frames, d_count, (uint32_t)std::min<size_t>(count, 0xffffffffu),
+    frames_pack_kernel<<<8, 256, 0, st>>>(d_frames, d_count, (uint32_t)std::min<size_t>(count, 0xffffffffu),
                                                   d_block, (uint32_t)rows_cap);
     CK(c, cudaGetLastError());
     c->timing.other_launches++;
     return B200ADSB_OK;
 }
 
-int b200adsb_frames_merge_dev(b200adsb_ctx *c, const b200adsb_frame *d_gathered, size_t n_ranks,
+int b200adsb_frames_merge_dev(b200adsb_ctx *c, void *stream, const b200adsb_frame *d_gathered, size_t n_ranks,
                               size_t rows_cap, b200adsb_frame *d_out, size_t cap, uint32_t *d_n_out)
 {
+    cudaStream_t st = stream ? (cudaStream_t)stream : c ? c->stream : nullptr;
     if (!c || !d_gathered || !d_n_out || n_ranks == 0 || rows_cap == 0 || rows_cap > 0xfffffffeu || (!d_out && cap))
         return B200ADSB_ERR_BAD_ARG;
     int rc = bind(c);
     if (rc) return rc;
-    frames_merge_kernel<<<16, 256, 0, c->stream>>>(d_gathered, (uint32_t)n_ranks, (uint32_t)rows_cap, d_out,
+    frames_merge_kernel<<<16, 256, 0, st>>>(d_gathered, (uint32_t)n_ranks, (uint32_t)rows_cap, d_out,
                                                    (uint32_t)std::min<size_t>(cap, 0xffffffffu), d_n_out);
     CK(c, cudaGetLastError());
     c->timing.other_launches++;

@@ -67,8 +67,9 @@ class ShardedDemodulator:
 
     FRAME_BYTES = 28
 
-    def __init__(self, ctx, rank: int, world: int, group=None, event_rows: int = 4096, frame_rows: int = 2048):
+    def __init__(self, ctx, rank: int, world: int, group=None, event_rows: int = 1024, frame_rows: int = 2048):
         import torch
+        import torch.distributed as dist
 
         self.ctx, self.rank, self.world, self.group = ctx, rank, world, group
         self.event_rows, self.frame_rows = event_rows, frame_rows
@@ -79,6 +80,13 @@ class ShardedDemodulator:
         self.fgathered = torch.zeros((world * (frame_rows + 1) * self.FRAME_BYTES,), dtype=torch.uint8, device=dev)
         self.n_out = torch.zeros((2,), dtype=torch.int32, device=dev)
         self.position = 0          # stream position (in global buffers) of the next batch
+        # The frame gather depends on nothing but its batch's resolve, and only the emitter waits for it: it
+        # runs on a side stream with a communicator of its own, off the scan -> exchange -> resolve critical path
+        # (on the main stream it cost 0.075 ms per step at N = 8, profiles/r2).
+        self.fstream = torch.cuda.Stream(device=dev)
+        self.fgroup = dist.new_group(backend=dist.get_backend(group)) if world > 1 else None
+        self.ev_resolved = torch.cuda.Event()
+        self.ev_packed = torch.cuda.Event()
 
     def _exchange_events(self, poisoned: bool = False) -> None:
         import torch.distributed as dist
@@ -132,16 +140,28 @@ class ShardedDemodulator:
 
     def gather_frames(self, frames_ptr: int, out_ptr: int, cap: int, count: int = 0, result_ptr: int = 0):
         """The ranks' frames of the last step -> the single stream in (global buffer, j) order with global
-        buffer indices, on EVERY rank (any of them can be the emitting one), enqueue-only.  count: frames
-        this rank holds (synchronous step) or result_ptr: the step_async outcome (its word 0 is the count).
-        Returns the device tensor n_out = [frames, overflow] to read after a stream sync."""
+        buffer indices, on EVERY rank (any of them can be the emitting one).  Enqueue-only, on the side stream
+        `self.fstream`: pack waits for the step's resolve; the main stream only waits for the pack (so that the
+        next batch may overwrite the frame array).  count: frames this rank holds (synchronous step) or
+        result_ptr: the step_async outcome (its word 0 is the count).  Returns the device tensor
+        n_out = [frames, overflow]; synchronise `fstream` (or the device) before reading it or the output."""
+        import torch
         import torch.distributed as dist
 
-        self.ctx.frames_pack_dev(frames_ptr, self.fblock.data_ptr(), self.frame_rows, count=count, count_ptr=result_ptr)
+        main = torch.cuda.current_stream()
+        self.ev_resolved.record(main)
+        self.fstream.wait_event(self.ev_resolved)
+        fs = self.fstream.cuda_stream
+        self.ctx.frames_pack_dev(frames_ptr, self.fblock.data_ptr(), self.frame_rows, count=count, count_ptr=result_ptr,
+                                 stream=fs)
+        self.ev_packed.record(self.fstream)
+        main.wait_event(self.ev_packed)
         if self.world > 1:
-            dist.all_gather_into_tensor(self.fgathered, self.fblock, group=self.group)
+            with torch.cuda.stream(self.fstream):
+                dist.all_gather_into_tensor(self.fgathered, self.fblock, group=self.fgroup)
             src = self.fgathered
         else:
             src = self.fblock
-        self.ctx.frames_merge_dev(src.data_ptr(), self.world, self.frame_rows, out_ptr, cap, self.n_out.data_ptr())
+        self.ctx.frames_merge_dev(src.data_ptr(), self.world, self.frame_rows, out_ptr, cap, self.n_out.data_ptr(),
+                                  stream=fs)
         return self.n_out

@@ -209,10 +209,12 @@ int b200adsb_resolve_batch_dev(b200adsb_ctx *ctx, b200adsb_frame *d_out, size_t 
  * sizeof(b200adsb_frame): row 0 = {u32 count, 0...}; the blocks are all-gathered; merge writes the single
  * ordered stream with GLOBAL buffer indices (round robin: global = local * n_ranks + rank) to d_out and
  * d_n_out[0] = frames, d_n_out[1] = 1 if a rank had more than rows_cap frames or the total exceeds cap.
- * count: *d_count (device) if d_count != NULL, else `count`.  Enqueue-only, on the context's stream. */
-int b200adsb_frames_pack_dev(b200adsb_ctx *ctx, const b200adsb_frame *d_frames, const uint32_t *d_count,
-                             size_t count, b200adsb_frame *d_block, size_t rows_cap);
-int b200adsb_frames_merge_dev(b200adsb_ctx *ctx, const b200adsb_frame *d_gathered, size_t n_ranks,
+ * count: *d_count (device) if d_count != NULL, else `count`.  Enqueue-only, on `stream` (a cudaStream_t;
+ * NULL = the context's stream): the gather depends on nothing but the batch's resolve and nothing but the
+ * emitter waits for it, so it can run on a side stream while the next batch is scanned. */
+int b200adsb_frames_pack_dev(b200adsb_ctx *ctx, void *stream, const b200adsb_frame *d_frames,
+                             const uint32_t *d_count, size_t count, b200adsb_frame *d_block, size_t rows_cap);
+int b200adsb_frames_merge_dev(b200adsb_ctx *ctx, void *stream, const b200adsb_frame *d_gathered, size_t n_ranks,
                               size_t rows_cap, b200adsb_frame *d_out, size_t cap, uint32_t *d_n_out);
 
 /* enqueue-only forms (no host round trip; outcome in d_result as for

@@ -61,6 +61,7 @@ def main():
         members = o.members()
 
     def merged_frames():
+        sh.fstream.synchronize()          # the gather runs on the side stream
         n = sh.n_out.cpu().numpy()
         assert n[1] == 0, n
         return tuples(merged[: int(n[0])].cpu().numpy())
