@@ -12,6 +12,10 @@
 // (b200adsb_demod_iq_batch_submit / _wait); frames leave in the same order as from the serial loop
 // (--serial keeps that one for comparison).
 //
+// Command line (main.rs:33-67): --host --port --driver --driver-extra (repeatable) --custom-config --quiet
+// with the reference's defaults and its configuration layering (sdrconfig.hpp; main.rs:72-86,106): the
+// entry selected by --driver is reported the way the reference narrates it, and a driver without an
+// entry is an error as there.  --print-config stops after that (no GPU needed).
 // Sources:  --file capture.iq   the reference's capture format (utils.rs:8-40: im, re pairs)
 //           --raw path | -      raw interleaved CS16 (re, im), e.g. a pipe from an SDR tool
 // --batch K collects K reads into one b200adsb_demod_iq_batch call (identical frames, in order).
@@ -23,6 +27,7 @@
 
 #include "avr_server.hpp"
 #include "dump1090_rs.hpp"
+#include "sdrconfig.hpp"
 
 using namespace dump1090_rs;
 
@@ -30,6 +35,10 @@ struct Options {
     std::string host = "127.0.0.1";     // main.rs:33-40 defaults
     int port = 30002;
     bool quiet = false;
+    std::string driver = "rtlsdr";      // main.rs:49-55
+    std::vector<std::string> driver_extra;
+    std::optional<std::string> custom_config;
+    bool print_config = false;
     std::string file, raw;
     std::size_t mtu = MODES_MAG_BUF_SAMPLES, batch = 1;
     int wait_clients = 0;               // test aid: do not start before this many clients are connected
@@ -51,6 +60,10 @@ static bool parse(int argc, char **argv, Options &o)
         if (a == "--host") o.host = val("--host");
         else if (a == "--port") o.port = std::atoi(val("--port"));
         else if (a == "--quiet") o.quiet = true;
+        else if (a == "--driver") o.driver = val("--driver");
+        else if (a == "--driver-extra") o.driver_extra.push_back(val("--driver-extra"));
+        else if (a == "--custom-config") o.custom_config = std::string(val("--custom-config"));
+        else if (a == "--print-config") o.print_config = true;
         else if (a == "--file") o.file = val("--file");
         else if (a == "--raw") o.raw = val("--raw");
         else if (a == "--mtu") o.mtu = (std::size_t)std::atoll(val("--mtu"));
@@ -60,7 +73,8 @@ static bool parse(int argc, char **argv, Options &o)
         else if (a == "--frame-cap") o.frame_cap = (std::size_t)std::atoll(val("--frame-cap"));
         else return false;
     }
-    return (!o.file.empty() || !o.raw.empty()) && o.mtu >= 1 && o.mtu <= MODES_MAG_BUF_SAMPLES && o.batch >= 1;
+    return (o.print_config || !o.file.empty() || !o.raw.empty()) && o.mtu >= 1 && o.mtu <= MODES_MAG_BUF_SAMPLES &&
+           o.batch >= 1;
 }
 
 int main(int argc, char **argv)
@@ -69,10 +83,26 @@ int main(int argc, char **argv)
     if (!parse(argc, argv, opt)) {
         std::fprintf(stderr,
                      "usage: %s (--file capture.iq | --raw path|-) [--host 127.0.0.1] [--port 30002] [--quiet]\n"
+                     "          [--driver rtlsdr] [--driver-extra k=v]... [--custom-config file.toml] [--print-config]\n"
                      "          [--mtu samples<=131072] [--batch reads] [--wait-clients n] [--serial] [--frame-cap n]\n", argv[0]);
         return 2;
     }
     try {
+        // configuration layering and driver selection (main.rs:72-120)
+        std::string note;
+        const SdrConfig config = layered_config(opt.custom_config, &note);
+        if (!note.empty())
+            std::printf("%s\n", note.c_str());
+        std::printf("[-] using soapysdr driver_args: %s\n", driver_args(opt.driver, opt.driver_extra).c_str());
+        const Sdr *sdr = find_sdr(config, opt.driver);
+        if (!sdr) {
+            std::fprintf(stderr, "[-] selected --driver gain values not found in custom or default config\n");
+            return 1;
+        }
+        std::printf("%s", describe(*sdr).c_str());
+        std::fflush(stdout);
+        if (opt.print_config)
+            return 0;
         // the sample source
         std::vector<Complex16> capture;
         std::size_t cap_pos = 0;
