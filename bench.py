@@ -288,6 +288,8 @@ def main() -> int:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (configs0, configs3, strong_8192, ...)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "symm", "nccl"],
+                    help="N>1 event exchange: peer stores into symmetric memory from the library's kernels, or NCCL")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -330,7 +332,7 @@ def main() -> int:
     frames = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
     merged = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
     n_frames = [0]
-    sh = sharded.ShardedDemodulator(ctx, rank, world, frame_rows=2048)
+    sh = sharded.ShardedDemodulator(ctx, rank, world, frame_rows=2048, exchange=args.exchange)
 
     # The timed steps are queued back to back with the enqueue-only entry points: the batch outcome {frames,
     # failure flags, ...} stays on the device and is checked after the timed region; warm-up steps use the
@@ -443,7 +445,7 @@ def main() -> int:
     if world > 1:
         n_out = sh.n_out.cpu().numpy()
         stream_frames = frames_to_tuples(merged[: int(n_out[0])].cpu().numpy())
-        remote_events = int(sum(int(sh.gathered[r * sh.event_rows, 0].item()) for r in range(world) if r != rank))
+        remote_events = int(sum(c for r, c in enumerate(sh.last_event_counts()) if r != rank))
         gather_overflow = int(n_out[1])
     else:
         stream_frames = frames_to_tuples(frames[: n_frames[0]].cpu().numpy())
@@ -564,24 +566,25 @@ def main() -> int:
 
         if rank == 0:
             from dump1090_rs_b200 import synth
-            # ---- configs[3]: injected DF17 at 1 / 10 / 100 per buffer (16 distinct buffers repeated over 256)
+            # ---- configs[3]: injected DF17 at 1 / 10 / 100 per buffer (16 distinct buffers repeated over the batch)
             sub["configs3"] = {}
             for m in (1, 10, 100):
                 inj = torch.from_numpy(synth.make_batch(SEED, 16, msgs_per_buffer=m)).to(dev)
-                iq_m = inj.repeat(16, 1, 1)
+                n3 = min(nb, 1000)
+                iq_m = inj.repeat((n3 + 15) // 16, 1, 1)[:n3].contiguous()
                 c3 = d.Context(local, stream.cuda_stream)
                 c3.set_option(_ffi.OPT_PROFILE, 1)
                 res3 = torch.zeros((10, 4), dtype=torch.int32, device=dev)
                 for _ in range(3):
                     c3.icao_flush()
-                    nfm = c3.demod_iq_batch_ptr(iq_m.data_ptr(), 256, SAMPLES, SAMPLES, frames.data_ptr(), cap)
+                    nfm = c3.demod_iq_batch_ptr(iq_m.data_ptr(), n3, SAMPLES, SAMPLES, frames.data_ptr(), cap)
                 torch.cuda.synchronize()
                 c3.timing(reset=True)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 for k in range(10):
                     c3.icao_flush()
-                    c3.demod_iq_batch_async_ptr(iq_m.data_ptr(), 256, SAMPLES, SAMPLES, frames.data_ptr(), cap, res3[k].data_ptr())
+                    c3.demod_iq_batch_async_ptr(iq_m.data_ptr(), n3, SAMPLES, SAMPLES, frames.data_ptr(), cap, res3[k].data_ptr())
                 e1.record()
                 torch.cuda.synchronize()
                 c3.sync()
@@ -589,11 +592,11 @@ def main() -> int:
                 r3 = res3.cpu().numpy()
                 ms3 = e0.elapsed_time(e1)
                 sub["configs3"][str(m)] = {
-                    "value": 256 * SAMPLES * 10 / (ms3 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms3 / 10,
+                    "value": n3 * SAMPLES * 10 / (ms3 * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms3 / 10,
                     "frames_per_step": nfm, "verified": bool((r3[:, 1] == 0).all() and (r3[:, 0] == nfm).all()),
                     "scan_ms_per_step": t3["scan_ms"] / 10, "resolve_ms_per_step": t3["resolve_ms"] / 10,
                     "roofline_frac": 4.0 * t3["samples"] / (t3["scan_ms"] * 1e-3) / 1e9 / peak if t3["scan_ms"] else None,
-                    "buffers": 256}
+                    "buffers": n3}
                 c3.close()
                 del iq_m, inj
             # ---- configs[0]: the cargo bench '01' case, one capture per call (benches/demod_benchmark.rs:7-12,23)
@@ -636,8 +639,8 @@ def main() -> int:
                        "frames_per_step_rank0": n_frames[0],
                        "step_call": ("synchronous ABI calls (host round trips inside every step)" if not queued_steps else
                                      ("b200adsb_demod_iq_batch_dev_async" if world == 1 else
-                                      "b200adsb_scan_batch_dev_async + events all-gather + b200adsb_resolve_batch_dev_async + "
-                                      "frames pack / all-gather / merge on a side stream")
+                                      "b200adsb_scan_batch_dev_async + event exchange (" + sh.exchange + ") + "
+                                      "b200adsb_resolve_batch_dev_async + frames pack / all-gather / merge on a side stream")
                                      + " (steps queued back to back, outcomes checked after the timed region)")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "parity_on_sample": None if parity is None else parity["ok"], "parity": parity,

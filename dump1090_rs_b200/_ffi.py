@@ -113,6 +113,11 @@ _PROTOS = {
     "b200adsb_events_import_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200adsb_events_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "b200adsb_events_import_packed_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]),
+    "b200adsb_events_symm_words": (C.c_size_t, [C.c_size_t, C.c_size_t]),
+    "b200adsb_events_push_symm_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64,
+                                                C.c_uint32]),
+    "b200adsb_events_import_symm_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                                  C.c_uint64]),
     "b200adsb_frames_pack_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                            C.c_size_t]),
     "b200adsb_frames_merge_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,

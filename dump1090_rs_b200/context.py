@@ -174,6 +174,15 @@ class Context:
         self._check(self._L.b200adsb_events_import_packed_dev(self._h, gathered_ptr, n_ranks, rows_per_rank,
                                                               skip_rank), "events_import_packed")
 
+    def events_push_symm_dev(self, peer_bufs_dev_ptr: int, rank: int, n_ranks: int, rows_per_rank: int, epoch: int,
+                             force_flags: int = 0):
+        self._check(self._L.b200adsb_events_push_symm_dev(self._h, peer_bufs_dev_ptr, rank, n_ranks, rows_per_rank,
+                                                          epoch, force_flags), "events_push_symm")
+
+    def events_import_symm_dev(self, local_buf_ptr: int, rank: int, n_ranks: int, rows_per_rank: int, epoch: int):
+        self._check(self._L.b200adsb_events_import_symm_dev(self._h, local_buf_ptr, rank, n_ranks, rows_per_rank,
+                                                            epoch), "events_import_symm")
+
     def frames_pack_dev(self, frames_ptr: int, block_ptr: int, rows_cap: int, count: int = 0, count_ptr: int = 0,
                         stream: int = 0):
         self._check(self._L.b200adsb_frames_pack_dev(self._h, stream or None, frames_ptr or None, count_ptr or None,

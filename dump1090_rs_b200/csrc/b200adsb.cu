@@ -977,6 +977,43 @@ int b200adsb_events_import_packed_dev(b200adsb_ctx *c, const uint64_t *d_gathere
     return B200ADSB_OK;
 }
 
+size_t b200adsb_events_symm_words(size_t n_ranks, size_t rows_per_rank)
+{
+    return 2 * n_ranks + 2 * n_ranks * rows_per_rank * 2;
+}
+
+int b200adsb_events_push_symm_dev(b200adsb_ctx *c, uint64_t *const *d_peer_bufs, size_t rank, size_t n_ranks,
+                                  size_t rows_per_rank, uint64_t epoch, uint32_t force_flags)
+{
+    if (!c || !d_peer_bufs || n_ranks == 0 || n_ranks > 256 || rank >= n_ranks || rows_per_rank < 2 || epoch == 0)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    events_push_symm_kernel<<<16, 256, 0, c->stream>>>(c->d_ev_keys, c->d_ev_ord, c->d_ev_used, c->d_counters,
+                                                        (unsigned long long *const *)d_peer_bufs, (uint32_t)rank,
+                                                        (uint32_t)n_ranks, (uint32_t)rows_per_rank, epoch,
+                                                        force_flags & kBadMask);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+int b200adsb_events_import_symm_dev(b200adsb_ctx *c, uint64_t *d_local_buf, size_t rank, size_t n_ranks,
+                                    size_t rows_per_rank, uint64_t epoch)
+{
+    if (!c || !d_local_buf || n_ranks == 0 || n_ranks > 256 || rank >= n_ranks || rows_per_rank < 2 || epoch == 0)
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    events_import_symm_kernel<<<16, 256, 0, c->stream>>>((unsigned long long *)d_local_buf, (uint32_t)rank,
+                                                          (uint32_t)n_ranks, (uint32_t)rows_per_rank, epoch,
+                                                          c->d_ev_keys, c->d_ev_ord, c->d_ev_used, kEvSlots - 1,
+                                                          c->d_counters);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
 int b200adsb_frames_pack_dev(b200adsb_ctx *c, void *stream, const b200adsb_frame *d_frames, const uint32_t *d_count,
                              size_t count, b200adsb_frame *d_block, size_t rows_cap)
 {

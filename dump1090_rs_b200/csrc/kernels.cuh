@@ -610,6 +610,113 @@ __global__ void events_import_packed_kernel(const unsigned long long *gathered, 
     }
 }
 
+// ---- the same exchange fused with its transport: no NCCL call between scan and resolve.
+// Every rank owns a buffer in symmetric (peer-mapped) memory, all with the same layout:
+//   u64 flags[2][world]                      flag [p][r] = epoch of the last block rank r pushed with parity p
+//   u64 blocks[2][world][rows_per_rank][2]   packed rows as above
+// events_push_symm_kernel packs this rank's events and stores them straight into block [p][rank] of EVERY
+// rank's buffer over NVLink (peer stores), fences, and the last block to finish raises flag [p][rank] on
+// every rank.  events_import_symm_kernel (next launch on the same stream) waits until all `world` flags of
+// parity p have reached the epoch, then merges the blocks found locally.  Two parities: a rank can be at
+// most one exchange ahead of a peer (its next push needs the peer's push of this epoch), so the block a
+// slow peer is still reading is never the one being overwritten.
+__device__ __forceinline__ unsigned long long *symm_block(unsigned long long *base, uint32_t world, uint32_t rows,
+                                                          uint32_t parity, uint32_t r)
+{
+    return base + 2ull * world + 2ull * rows * ((unsigned long long)parity * world + r);
+}
+__global__ void events_push_symm_kernel(const uint32_t *ev_keys, const unsigned long long *ev_ord,
+                                        const uint32_t *ev_used, uint32_t *counters,
+                                        unsigned long long *const *peer_bufs, uint32_t rank, uint32_t world,
+                                        uint32_t rows_per_rank, unsigned long long epoch, uint32_t force_flags)
+{
+    __shared__ uint32_t s_last;
+    const uint32_t parity = (uint32_t)(epoch & 1ull);
+    const uint32_t n = counters[C_EV_USED];
+    const uint32_t m = min(n, rows_per_rank - 1);
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        uint32_t fl = (counters[C_FLAGS] & kBadMask) | force_flags;
+        if (n > rows_per_rank - 1) {
+            fl |= F_EV_OVF;
+            if (threadIdx.x == 0)
+                atomicOr(&counters[C_FLAGS], F_EV_OVF);
+        }
+        unsigned long long *dst = symm_block(peer_bufs[threadIdx.x], world, rows_per_rank, parity, rank);
+        dst[0] = n;
+        dst[1] = fl;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const uint32_t h = ev_used[i];
+        const unsigned long long key = ev_keys[h], ord = ev_ord[h];
+        for (uint32_t q = 0; q < world; q++) {
+            unsigned long long *dst = symm_block(peer_bufs[q], world, rows_per_rank, parity, rank);
+            dst[2ull * (i + 1)] = key;
+            dst[2ull * (i + 1) + 1] = ord;
+        }
+    }
+    __threadfence_system();                    // this thread's peer stores before the ticket
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(&counters[C_TICKET], 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < world) {
+            unsigned long long *flag = peer_bufs[threadIdx.x] + (unsigned long long)parity * world + rank;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+        }
+        if (threadIdx.x == 0)
+            counters[C_TICKET] = 0;
+    }
+}
+__global__ void events_import_symm_kernel(unsigned long long *local_buf, uint32_t rank, uint32_t world,
+                                          uint32_t rows_per_rank, unsigned long long epoch, uint32_t *ev_keys,
+                                          unsigned long long *ev_ord, uint32_t *ev_used, uint32_t mask,
+                                          uint32_t *counters)
+{
+    __shared__ uint32_t s_timeout;
+    const uint32_t parity = (uint32_t)(epoch & 1ull);
+    if (threadIdx.x == 0)
+        s_timeout = 0;
+    __syncthreads();
+    if (threadIdx.x < world) {
+        const unsigned long long *flag = local_buf + (unsigned long long)parity * world + threadIdx.x;
+        const long long t0 = clock64();
+        for (;;) {
+            unsigned long long v;
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v >= epoch)
+                break;
+            if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer died; fail the batch instead of hanging
+                s_timeout = 1;
+                break;
+            }
+            __nanosleep(200);
+        }
+    }
+    __syncthreads();
+    if (s_timeout) {
+        if (blockIdx.x == 0 && threadIdx.x == 0)
+            atomicOr(&counters[C_FLAGS], F_REMOTE_BAD);
+        return;
+    }
+    for (uint32_t r = 0; r < world; r++) {
+        if (r == rank)
+            continue;
+        // (written by a peer over NVLink: read through L2, never from this SM's L1)
+        const unsigned long long *rows = symm_block(local_buf, world, rows_per_rank, parity, r);
+        const unsigned long long n = __ldcg(rows);
+        if (n > rows_per_rank - 1 || (__ldcg(rows + 1) & kBadMask) != 0ull) {
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                atomicOr(&counters[C_FLAGS], F_REMOTE_BAD);
+            continue;
+        }
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += gridDim.x * blockDim.x)
+            event_add(ev_keys, ev_ord, ev_used, mask, counters, (uint32_t)__ldcg(rows + 2ull * (i + 1)),
+                      __ldcg(rows + 2ull * (i + 1) + 1));
+    }
+}
+
 __global__ void events_import_kernel(const unsigned long long *pairs, uint32_t n, uint32_t *ev_keys,
                                      unsigned long long *ev_ord, uint32_t *ev_used, uint32_t mask,
                                      uint32_t *counters)

@@ -67,7 +67,11 @@ class ShardedDemodulator:
 
     FRAME_BYTES = 28
 
-    def __init__(self, ctx, rank: int, world: int, group=None, event_rows: int = 1024, frame_rows: int = 2048):
+    def __init__(self, ctx, rank: int, world: int, group=None, event_rows: int = 1024, frame_rows: int = 2048,
+                 exchange: str = "auto"):
+        """exchange: "symm" = the event exchange as peer stores into symmetric memory from the library's own
+        kernels (b200adsb_events_push_symm_dev / _import_symm_dev; no NCCL call between scan and resolve),
+        "nccl" = pack + all_gather_into_tensor + import, "auto" = symm when torch can set it up."""
         import torch
         import torch.distributed as dist
 
@@ -80,6 +84,20 @@ class ShardedDemodulator:
         self.fgathered = torch.zeros((world * (frame_rows + 1) * self.FRAME_BYTES,), dtype=torch.uint8, device=dev)
         self.n_out = torch.zeros((2,), dtype=torch.int32, device=dev)
         self.position = 0          # stream position (in global buffers) of the next batch
+        self.exchange = "nccl"
+        self.epoch = 0
+        if world > 1 and exchange in ("auto", "symm"):
+            try:
+                self._setup_symm(dev, group)
+                self.exchange = "symm"
+            except Exception as e:      # noqa: BLE001 -- any failure means "not available here"
+                if exchange == "symm":
+                    raise
+                self.symm_error = repr(e)[:200]
+        if world > 1:                   # every rank must have taken the same decision
+            flag = torch.tensor([1 if self.exchange == "symm" else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            self.exchange = "symm" if int(flag.item()) == 1 else "nccl"
         # The frame gather depends on nothing but its batch's resolve, and only the emitter waits for it: it
         # runs on a side stream with a communicator of its own, off the scan -> exchange -> resolve critical path
         # (on the main stream it cost 0.075 ms per step at N = 8, profiles/r2).
@@ -88,10 +106,36 @@ class ShardedDemodulator:
         self.ev_resolved = torch.cuda.Event()
         self.ev_packed = torch.cuda.Event()
 
+    def _setup_symm(self, dev, group) -> None:
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _ffi
+        words = int(_ffi.lib().b200adsb_events_symm_words(self.world, self.event_rows))
+        g = group if group is not None else dist.group.WORLD
+        try:
+            symm_mem.enable_symm_mem_for_group(g.group_name)
+        except Exception:               # noqa: BLE001 -- newer torch enables it implicitly
+            pass
+        self.symm = symm_mem.empty(words, dtype=torch.int64, device=dev)
+        self.symm.zero_()
+        torch.cuda.synchronize(dev)
+        self.symm_hdl = symm_mem.rendezvous(self.symm, g)
+        self.peer_bufs_dev = int(self.symm_hdl.buffer_ptrs_dev)
+        dist.barrier(group=group)       # nobody pushes before every buffer is zeroed
+
     def _exchange_events(self, poisoned: bool = False) -> None:
         import torch.distributed as dist
 
         if self.world <= 1:
+            return
+        if self.exchange == "symm":
+            self.epoch += 1
+            self.ctx.events_push_symm_dev(self.peer_bufs_dev, self.rank, self.world, self.event_rows, self.epoch,
+                                          force_flags=2 if poisoned else 0)
+            if not poisoned:
+                self.ctx.events_import_symm_dev(self.symm.data_ptr(), self.rank, self.world, self.event_rows, self.epoch)
             return
         if poisoned:
             # this rank's scan failed before the exchange: still take part in the collective, with a block
@@ -104,6 +148,16 @@ class ShardedDemodulator:
         dist.all_gather_into_tensor(self.gathered, self.rows, group=self.group)
         if not poisoned:
             self.ctx.events_import_packed_dev(self.gathered.data_ptr(), self.world, self.event_rows, self.rank)
+
+    def last_event_counts(self) -> list[int]:
+        """Events each rank published in the last exchange (diagnostics; synchronises)."""
+        if self.world <= 1:
+            return [0]
+        if self.exchange == "symm":
+            p = self.epoch & 1
+            base = 2 * self.world
+            return [int(self.symm[base + 2 * self.event_rows * (p * self.world + r)].item()) for r in range(self.world)]
+        return [int(self.gathered[r * self.event_rows, 0].item()) for r in range(self.world)]
 
     def step(self, iq_ptr: int, n_local: int, spb: int, stride: int, out_ptr: int, cap: int,
              n_total: int | None = None, counts_ptr: int = 0) -> int:

@@ -201,6 +201,19 @@ int b200adsb_events_import_dev(b200adsb_ctx *ctx, const uint64_t *d_pairs, size_
 int b200adsb_events_pack_dev(b200adsb_ctx *ctx, uint64_t *d_rows, size_t rows_cap);
 int b200adsb_events_import_packed_dev(b200adsb_ctx *ctx, const uint64_t *d_gathered, size_t n_ranks,
                                       size_t rows_per_rank, size_t skip_rank);
+/* The same exchange fused with its transport (no collective library call on the scan -> resolve path):
+ * every rank owns a buffer of b200adsb_events_symm_words(n_ranks, rows_per_rank) u64 in symmetric
+ * (peer-mapped, zero-initialised) device memory; d_peer_bufs is a DEVICE array of the n_ranks base
+ * pointers as seen from this rank.  push packs this rank's events and stores them into its slot of every
+ * rank's buffer over NVLink, then raises its flag there; import waits (on the device, bounded) for all
+ * n_ranks flags of this epoch and merges.  epoch: 1, 2, 3, ... identical on all ranks, one per exchange.
+ * force_flags: bad-batch flags to publish even though the local counters are clean (a rank whose scan
+ * failed before the exchange).  A peer that never arrives fails the batch (bit 4) instead of hanging. */
+size_t b200adsb_events_symm_words(size_t n_ranks, size_t rows_per_rank);
+int b200adsb_events_push_symm_dev(b200adsb_ctx *ctx, uint64_t *const *d_peer_bufs, size_t rank, size_t n_ranks,
+                                  size_t rows_per_rank, uint64_t epoch, uint32_t force_flags);
+int b200adsb_events_import_symm_dev(b200adsb_ctx *ctx, uint64_t *d_local_buf, size_t rank, size_t n_ranks,
+                                    size_t rows_per_rank, uint64_t epoch);
 int b200adsb_resolve_batch_dev(b200adsb_ctx *ctx, b200adsb_frame *d_out, size_t cap,
                                size_t *n_out, uint32_t *d_per_buffer_counts);
 

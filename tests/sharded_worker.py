@@ -31,7 +31,7 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx = d.Context(local, stream.cuda_stream)
-    sh = sharded.ShardedDemodulator(ctx, rank, world, frame_rows=1024)
+    sh = sharded.ShardedDemodulator(ctx, rank, world, frame_rows=1024, exchange=os.environ.get("B200ADSB_EXCHANGE", "auto"))
     cap = 8192
     frames = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
     merged = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
@@ -119,7 +119,7 @@ def main():
     ctx.close()
     dist.destroy_process_group()
     if rank == 0:
-        print("SHARDED_OK frames", [len(p) for p in per_batch])
+        print("SHARDED_OK exchange", sh.exchange, "frames", [len(p) for p in per_batch])
 
 
 if __name__ == "__main__":
