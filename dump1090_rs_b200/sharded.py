@@ -114,10 +114,6 @@ class ShardedDemodulator:
         from . import _ffi
         words = int(_ffi.lib().b200adsb_events_symm_words(self.world, self.event_rows))
         g = group if group is not None else dist.group.WORLD
-        try:
-            symm_mem.enable_symm_mem_for_group(g.group_name)
-        except Exception:               # noqa: BLE001 -- newer torch enables it implicitly
-            pass
         self.symm = symm_mem.empty(words, dtype=torch.int64, device=dev)
         self.symm.zero_()
         torch.cuda.synchronize(dev)
