@@ -368,6 +368,7 @@ def main() -> int:
 
     def timed_region(iq_t, nbuf, steps, queued, sample_clocks=True):
         step_no[0] = 0
+        barrier()              # ranks enter together (rank 0 may come from seconds of CPU-side work)
         for _ in range(args.warmup):
             run_step(iq_t, nbuf, False)
         barrier()
@@ -408,6 +409,21 @@ def main() -> int:
             ms_, tim_, clk_, ok = timed_region(iq_t, nbuf, steps, False)
         return ms_, tim_, clk_, queued
 
+    if world > 1 and sh.exchange == "symm":
+        # one trial step: if the peer-memory exchange does not work on this box (every rank then fails the
+        # batch together), the NCCL exchange takes over
+        barrier()
+        bad = 0
+        try:
+            run_step(iq, nb, False)
+            ctx.sync()
+        except _ffi.B200AdsbError:
+            bad = 1
+        flag = torch.tensor([bad], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            sh.exchange = "nccl"
+            ctx.async_acknowledge()
     ms, tim, clk, queued_steps = measure(iq, nb, args.steps)
     total_samples = nb * SAMPLES * world
     value = total_samples * args.steps / (ms * 1e-3) / 1e6

@@ -687,7 +687,7 @@ __global__ void events_import_symm_kernel(unsigned long long *local_buf, uint32_
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
             if (v >= epoch)
                 break;
-            if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer died; fail the batch instead of hanging
+            if (clock64() - t0 > 60000000000ll) {  // ~30 s: a peer died; fail the batch instead of hanging
                 s_timeout = 1;
                 break;
             }

@@ -1,7 +1,6 @@
 #!/bin/bash
 # N = 2, 4, 8 on one 8-GPU box (run under gpurun --gpus 8): the driver's scaling bench + the sharded GPU test
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_sharded_gpu.py -q -m gpu 2>&1 | tail -3
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29559 \
    bench.py --gpus 8 --steps 20 --no-sub --no-e2e --no-cpu --exchange nccl > gpurun_out/scale_n8_nccl.json 2> gpurun_out/scale_n8_nccl.err
 python -c "
