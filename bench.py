@@ -444,7 +444,7 @@ def main() -> int:
             pass
         return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic,
-                "kernel": "scan7_kernel<false>", "kernel_ms_per_launch": tim_["scan_ms"] / launches,
+                "kernel": "scan7_kernel<false, 7384, true>", "kernel_ms_per_launch": tim_["scan_ms"] / launches,
                 "algorithmic_bytes_per_launch": 4.0 * tim_["samples"] / launches, "peak_source": peak_src,
                 "kernel_share_of_step": (tim_["scan_ms"] / ms_) if ms_ else None,
                 "kernel_ms_per_step": tim_["scan_ms"] / steps,

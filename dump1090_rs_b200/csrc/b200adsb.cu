@@ -347,10 +347,21 @@ int launch_scan(b200adsb_ctx *c, uint32_t b0, uint32_t nb)
     if (grid == 0)
         return B200ADSB_OK;
     prof_begin(c, c->scan_events);
+    // the compile-time forms: default tile (shared memory plan as immediates), and on top of it a batch of
+    // whole standard buffers (length, tiles per buffer, alignment and carry tests folded)
+    const bool std_batch = !q.from_mag && q.T == kDefaultTile && !q.lengths && q.spb == (uint32_t)kMaxSamples &&
+                           p.vec_ok && !p.carry;
     if (q.from_mag)
-        scan7_kernel<true><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
+        scan7_kernel<true, 0, false><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
+#ifndef B200_SCAN7_SPECIALISE
+#define B200_SCAN7_SPECIALISE 2     // A/B builds: 0 = generic kernel only, 1 = + fixed tile, 2 = + standard batch
+#endif
+    else if (B200_SCAN7_SPECIALISE >= 2 && std_batch)
+        scan7_kernel<false, kDefaultTile, true><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
+    else if (B200_SCAN7_SPECIALISE >= 1 && q.T == kDefaultTile)
+        scan7_kernel<false, kDefaultTile, false><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
     else
-        scan7_kernel<false><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
+        scan7_kernel<false, 0, false><<<grid, k7Threads, L7.bytes, c->stream>>>(P7);
     prof_end(c, c->scan_events);
     CK(c, cudaGetLastError());
     c->timing.scan_launches++;
@@ -671,10 +682,14 @@ int b200adsb_ctx_create(b200adsb_ctx **out, int device, void *stream)
     CKC(cudaSetDevice(device));
     {   // the scan kernel's launch attributes, once: room for the largest tile, all of L1 as shared memory
         const int max_smem = (int)Scan7Smem(kMaxTile).bytes;
-        CKC(cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CKC(cudaFuncSetAttribute(scan7_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        CKC(cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-        CKC(cudaFuncSetAttribute(scan7_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        auto prep = [&](const void *fn) {
+            return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) == cudaSuccess &&
+                   cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess;
+        };
+        if (!prep((const void *)scan7_kernel<true, 0, false>) || !prep((const void *)scan7_kernel<false, 0, false>) ||
+            !prep((const void *)scan7_kernel<false, kDefaultTile, false>) ||
+            !prep((const void *)scan7_kernel<false, kDefaultTile, true>))
+            return fail(B200ADSB_ERR_CUDA);
     }
     if (stream) {
         c->stream = (cudaStream_t)stream;

@@ -61,7 +61,9 @@ constexpr int k7ListCap = 1024;             // template matches gated per round 
 struct Scan7Smem {
     int NG, WP, nw, mag_len, list_cap;
     size_t off_planes, off_surv, off_masks, off_list, off_cand, bytes;
-    __host__ __device__ explicit Scan7Smem(int T)
+    __host__ __device__ constexpr explicit Scan7Smem(int T)
+        : NG(0), WP(0), nw(0), mag_len(0), list_cap(0), off_planes(0), off_surv(0), off_masks(0), off_list(0),
+          off_cand(0), bytes(0)
     {
         NG = (T + kHaloTot + k7Group - 1) / k7Group;
         mag_len = NG * k7Group + 32;
@@ -297,11 +299,31 @@ __device__ __forceinline__ void p3a_rows(const uint32_t *planes, int WP, int nwq
     }
 }
 
-template <bool FROM_MAG>
-__global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel(const Scan7Params P)
+// TC: tile size fixed at compile time (0: taken from the parameters).  For the default tile the whole shared
+// memory plan -- plane row stride, offsets, list capacity, mask row width -- becomes immediates (-7 % static
+// instructions, -4 % time).  STD: a batch of whole standard buffers (131,072 samples each, no per-buffer
+// lengths, 16-byte aligned, no carry): buffer length, tiles per buffer and the alignment test fold as well.
+template <bool FROM_MAG, int TC, bool STD>
+__global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel(const Scan7Params Pin)
 {
+    static_assert(!STD || (TC != 0 && !FROM_MAG), "the standard-batch form fixes the tile as well");
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr Scan7Smem LC(TC ? TC : 8);
+    constexpr int kStdTpb = TC ? (kMaxSamples + TC - 1) / TC : 1;
+    struct {
+        const ScanParams &s;
+        uint32_t off_planes, off_surv, off_masks, off_list, off_cand;
+        int WP, nw, list_cap, Wrow, inv_Wrow;
+    } P = {Pin.s,
+           TC ? (uint32_t)LC.off_planes : Pin.off_planes, TC ? (uint32_t)LC.off_surv : Pin.off_surv,
+           TC ? (uint32_t)LC.off_masks : Pin.off_masks, TC ? (uint32_t)LC.off_list : Pin.off_list,
+           TC ? (uint32_t)LC.off_cand : Pin.off_cand, TC ? LC.WP : Pin.WP, TC ? LC.nw : Pin.nw,
+           TC ? LC.list_cap : Pin.list_cap, TC ? (LC.NG + 1) / 2 : Pin.Wrow,
+           TC ? (65536 + (LC.NG + 1) / 2 - 1) / ((LC.NG + 1) / 2) : Pin.inv_Wrow};
     const ScanParams &p = P.s;
+    const int Tc = TC ? TC : p.T;
+    const int tpb = STD ? kStdTpb : p.tiles_per_buffer;
+    const int vec_ok = STD ? 1 : p.vec_ok;
     uint16_t *mag = reinterpret_cast<uint16_t *>(smem);
     uint32_t *fb = reinterpret_cast<uint32_t *>(smem);                      // P4: staged fields (mag is dead)
     uint32_t *planes = reinterpret_cast<uint32_t *>(smem + P.off_planes);   // [7][12][WP]
@@ -325,17 +347,17 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     if (blockIdx.x < 148u * B200_SCAN7_MIN_BLOCKS)
         __nanosleep((blockIdx.x / 148u) * B200_SCAN7_STAGGER);
 #endif
-    const uint32_t tile = p.b0 * (uint32_t)p.tiles_per_buffer + blockIdx.x;   // tile of the batch
-    const uint32_t b = tile / (uint32_t)p.tiles_per_buffer;
-    const int kt = (int)(tile - b * (uint32_t)p.tiles_per_buffer);
-    const int len = p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb;
-    const int tile_start = kt * p.T;
+    const uint32_t tile = p.b0 * (uint32_t)tpb + blockIdx.x;   // tile of the batch
+    const uint32_t b = tile / (uint32_t)tpb;
+    const int kt = (int)(tile - b * (uint32_t)tpb);
+    const int len = STD ? kMaxSamples : (p.lengths ? (int)min(p.lengths[b], p.spb) : (int)p.spb);
+    const int tile_start = kt * Tc;
     if (tile_start >= len) {
         if (tid == 0)
             p.tile_dir[tile] = make_uint2(0u, 0u);
         return;
     }
-    const int npos = min(p.T, len - tile_start);
+    const int npos = min(Tc, len - tile_start);
     const int NG = (npos + kHaloTot + k7Group - 1) / k7Group;   // groups actually needed
     const int WP = P.WP;
     const int nwq = (NG + 1) / 2;                                // plane words that carry data
@@ -354,7 +376,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     // ---- P1: dense phase (magnitudes, edges, correlator signs; see the header)
     {
         const CarrySrc cs{reinterpret_cast<const uint32_t *>(p.in), p.stride, p.lengths, p.spb, p.tails, p.counters,
-                          FROM_MAG ? 0 : p.carry};
+                          (FROM_MAG || STD) ? 0 : p.carry};
         const uint32_t *b32 = reinterpret_cast<const uint32_t *>(p.in) + (unsigned long long)b * p.stride;
         const uint16_t *d16 = reinterpret_cast<const uint16_t *>(p.in) + (unsigned long long)b * p.stride;
         const int s0 = tile_start - (kTrailing + kHaloFront);    // sample index of tile magnitude 0
@@ -375,7 +397,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                     st.acc[e][f] = 0;
             // whole warp inside the buffer and 16-byte aligned: plain LDG.128 with one slot of prefetch
             const int g_lo = k7Group * gbase, g_hi = k7Group * (gbase + k7GroupsPerWarp + 2) + 4;
-            const bool fast = !FROM_MAG && p.vec_ok && s0 + g_lo >= 0 && s0 + g_hi <= len;
+            const bool fast = !FROM_MAG && vec_ok && s0 + g_lo >= 0 && s0 + g_hi <= len;
             {
                 const int rb = k7Group * (G + 1);                  // first row of the next group
                 Row rbnd;

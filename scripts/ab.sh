@@ -10,7 +10,7 @@ if [ "$mode" = build ]; then
   while [ $# -gt 0 ]; do
     n=$1; f=$2; shift 2
     nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -std=c++17 -Xcompiler -fPIC -shared $f \
-      -Xptxas -v -o variants/lib_$n.so dump1090_rs_b200/csrc/b200adsb.cu 2>&1 | grep -A2 "scan7_kernelILb0" | grep -E "registers|spill" | sed "s/^/$n: /"
+      -Xptxas -v -o variants/lib_$n.so dump1090_rs_b200/csrc/b200adsb.cu 2>&1 | grep -A2 "scan7_kernelILb0ELi7384ELb1" | grep -E "registers|spill" | sed "s/^/$n: /"
   done
 else
   for round in 1 2 3; do
