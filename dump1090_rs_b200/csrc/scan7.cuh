@@ -529,14 +529,17 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             if (lane == 31 && incl)
                 base = (int)atomicAdd(&s_count, (uint32_t)incl);
             base = __shfl_sync(0xffffffffu, base, 31);
-            int off = base + incl - cnt;
+            // (mask word, bit) entries; the gate thread decodes.  Entries past the capacity are dropped here:
+            // the overflow pass below then gates every match in place.
+            const int off = base + incl - cnt;
+            const int take = min(cnt, max(P.list_cap - off, 0));
+            uint16_t *lp = list + off;
             uint32_t any = m.x;
-            while (any) {
-                const int bit = __ffs(any) - 1;
-                any &= any - 1;
-                if (off < P.list_cap)
-                    list[off] = (uint16_t)(i | (bit << 10));       // (mask word, bit); the gate thread decodes
-                off++;
+#pragma unroll 1
+            for (int k = 0; k < take; k++) {
+                const uint32_t bit = 31u - (uint32_t)__clz(any);
+                any ^= 1u << bit;
+                lp[k] = (uint16_t)((uint32_t)i | (bit << 10));
             }
         }
     }
@@ -647,12 +650,20 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             for (int h = 0; h < 2; h++) {
                 const int wi = 2 * tid + h;
                 uint32_t wv2 = (wi < P.nw) ? surv[wi] : 0u;
-                while (wv2) {
-                    const int bit = __ffs(wv2) - 1;
-                    wv2 &= wv2 - 1;
-                    if (off >= win && off < win + k7CandCap)
-                        cand[off - win] = (uint16_t)(wi * 32 + bit);
-                    off++;
+                if (C <= k7CandCap) {            // the usual case, one window: no range test per survivor
+                    while (wv2) {
+                        const int bit = __ffs(wv2) - 1;
+                        wv2 &= wv2 - 1;
+                        cand[off++] = (uint16_t)(wi * 32 + bit);
+                    }
+                } else {
+                    while (wv2) {
+                        const int bit = __ffs(wv2) - 1;
+                        wv2 &= wv2 - 1;
+                        if (off >= win && off < win + k7CandCap)
+                            cand[off - win] = (uint16_t)(wi * 32 + bit);
+                        off++;
+                    }
                 }
             }
         }
