@@ -477,6 +477,29 @@ def main() -> int:
         parity = {"ok": got == ref and gather_overflow == 0, "global_buffers": n_sig, "frames": len(ref),
                   "frames_whole_step": len(stream_frames), "events_from_other_ranks": remote_events}
 
+    # ---- and deep inside the batch (N = 1): stage-1 records of buffers sampled across the whole launch --
+    # survivor set and every (j, try-phase) classification -- against the oracle (frames are too rare in noise
+    # to say anything about buffer 500)
+    if rank == 0 and world == 1 and not args.no_cpu and parity is not None:
+        from oracle import oracle as O
+        pick = sorted(set(range(0, nb, max(nb // 11, 1))) | {nb - 1})[:13]
+        ctx.scan_batch_dev(iq.data_ptr(), nb, SAMPLES, SAMPLES, 0, 1)
+        rb, rr = ctx.debug_records_np(cap=max(nb * 2600, 1 << 16))
+        ctx.resolve_batch_dev(frames.data_ptr(), cap)
+        host = iq[pick].cpu().numpy()
+        o = O.Oracle()
+        deep_ok, n_rec = True, 0
+        norm = lambda w: [0 if (x >> 29) == 0 else x for x in w]
+        for k, b in enumerate(pick):
+            got = [(int(r[0]), norm([int(x) for x in r[1:]])) for r in rr[rb == b]]
+            ref = [(j, norm(w)) for j, w in o.records(o.to_mag(host[k]), cap=1 << 17)]
+            deep_ok = deep_ok and got == ref
+            n_rec += len(ref)
+        parity["sampled_buffers"] = pick
+        parity["stage1_records_checked"] = n_rec
+        parity["stage1_records_ok"] = deep_ok
+        parity["ok"] = parity["ok"] and deep_ok
+
     sub = {}
     # ---- e2e: host-buffer C-ABI call, H2D + D2H inside the timed region; and the H2D-only ceiling beside it
     e2e = None

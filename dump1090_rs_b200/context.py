@@ -246,15 +246,20 @@ class Context:
             return None
         return (MsgLen.Long if ln.value == 14 else MsgLen.Short, int(sc.value))
 
-    def debug_records(self, cap: int = 1 << 18):
-        """Stage-1 records of the pending batch (between scan_batch_dev and resolve_batch_dev):
-        [(buffer, j, [w4..w8])] in (buffer, j) order."""
+    def debug_records_np(self, cap: int = 1 << 18):
+        """Stage-1 records of the pending batch (between scan_batch_dev and resolve_batch_dev) as arrays:
+        buffers [n] and records [n, 6] = {j, w4..w8}, in (buffer, j) order."""
         bufs = np.zeros(cap, dtype=np.uint32)
         rec = np.zeros((cap, 6), dtype=np.uint32)
         n = C.c_size_t(0)
         self._check(self._L.b200adsb_debug_records(self._h, bufs.ctypes.data, rec.ctypes.data, cap, C.byref(n)),
                     "debug_records")
-        return [(int(bufs[i]), int(rec[i, 0]), [int(x) for x in rec[i, 1:]]) for i in range(n.value)]
+        return bufs[: n.value], rec[: n.value]
+
+    def debug_records(self, cap: int = 1 << 18):
+        """The same as a list [(buffer, j, [w4..w8])]."""
+        bufs, rec = self.debug_records_np(cap)
+        return [(int(bufs[i]), int(rec[i, 0]), [int(x) for x in rec[i, 1:]]) for i in range(len(bufs))]
 
     def async_acknowledge(self):
         self._check(self._L.b200adsb_async_acknowledge(self._h), "async_acknowledge")

@@ -720,3 +720,32 @@ def test_single_message_surface(pkg, ctx, oracle_mod, golden_frames):
             assert got is None, m.hex()
         else:
             assert got is not None and (14 if got[0] == pkg.demod_2400.MsgLen.Long else 7, got[1]) == (ln.value, sc.value), m.hex()
+
+
+def test_stage1_records_deep_in_a_large_batch(pkg, oracle_mod):
+    """Buffers far into a large device batch (tile indices in the thousands, pool offsets in the hundred
+    thousands): survivor set and record words of sampled buffers equal the oracle's -- parity of a big launch
+    beyond its first buffers."""
+    import torch
+    from dump1090_rs_b200 import synth
+    nb, spb = 384, 131072
+    d_iq = synth.noise_batch_torch(7, nb, device="cuda:0")
+    sample = [0, 1, 95, 200, 383]
+    inj = synth.make_batch(11, len(sample), msgs_per_buffer=40)
+    for k, b in enumerate(sample):
+        d_iq[b] = torch.from_numpy(inj[k]).to("cuda:0")
+    c = pkg.Context(0)
+    c.scan_batch_dev(d_iq.data_ptr(), nb, spb, spb, 0, 1)
+    bufs, rec = c.debug_records_np(cap=1 << 20)
+    out = torch.zeros((1 << 15, 28), dtype=torch.uint8, device="cuda:0")
+    c.resolve_batch_dev(out.data_ptr(), 1 << 15)
+    c.close()
+    assert len(bufs) > 300 * 1000                       # ~1400 survivors per buffer
+    assert (np.diff(bufs.astype(np.int64)) >= 0).all()  # (buffer, j) order
+    o = oracle_mod.Oracle()
+    host = d_iq[sample].cpu().numpy()
+    for k, b in enumerate(sample):
+        sel = bufs == b
+        got = [(int(r[0]), _norm_words([int(x) for x in r[1:]])) for r in rec[sel]]
+        ref = [(j, _norm_words(w)) for j, w in o.records(o.to_mag(host[k]), cap=1 << 17)]
+        assert got == ref, b
