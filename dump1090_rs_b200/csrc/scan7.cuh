@@ -398,6 +398,23 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             // whole warp inside the buffer and 16-byte aligned: plain LDG.128 with one slot of prefetch
             const int g_lo = k7Group * gbase, g_hi = k7Group * (gbase + k7GroupsPerWarp + 2) + 4;
             const bool fast = !FROM_MAG && vec_ok && s0 + g_lo >= 0 && s0 + g_hi <= len;
+            // rows travel global -> shared with cp.async (no registers held while in flight): the lane's
+            // private ring keeps B200_SCAN7_RING rows ahead of the one being processed.  The ring is primed
+            // BEFORE the group-closing row is fetched, so that the two DRAM latencies of a pass overlap.
+            const char *gsrc = reinterpret_cast<const char *>(b32 + s0 + r0) + 48 * (k7Slots - 1);
+            const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring) + 16u * (uint32_t)tid;
+            constexpr uint32_t kRingStride = 16u * k7Threads;
+            if (fast) {
+#pragma unroll
+                for (int d = 0; d < B200_SCAN7_RING; d++) {
+#if !(B200_ABL & 1)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + d * kRingStride),
+                                 "l"(gsrc - 48 * d));
+#endif
+                    asm volatile("cp.async.commit_group;");
+                }
+                gsrc -= 48 * B200_SCAN7_RING;
+            }
             {
                 const int rb = k7Group * (G + 1);                  // first row of the next group
                 Row rbnd;
@@ -415,20 +432,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             }
             uint16_t *mrow = mag + r0 + 12 * (k7Slots - 1);
             if (fast) {
-                // rows travel global -> shared with cp.async (no registers held while in flight): the lane's
-                // private ring keeps B200_SCAN7_RING rows ahead of the one being processed
-                const char *gsrc = reinterpret_cast<const char *>(b32 + s0 + r0) + 48 * (k7Slots - 1);
-                const uint32_t ring0 = (uint32_t)__cvta_generic_to_shared(ring) + 16u * (uint32_t)tid;
-                constexpr uint32_t kRingStride = 16u * k7Threads;
-#pragma unroll
-                for (int d = 0; d < B200_SCAN7_RING; d++) {
-#if !(B200_ABL & 1)
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring0 + d * kRingStride),
-                                 "l"(gsrc - 48 * d));
-#endif
-                    asm volatile("cp.async.commit_group;");
-                }
-                gsrc -= 48 * B200_SCAN7_RING;
                 uint32_t rp = ring0;
 #pragma unroll 1   // measured: 2 slots per iteration spill at 72 registers and cost 4 % (0.390 vs 0.373 ms)
                 for (int k = k7Slots - 1; k >= 0; k--) {
