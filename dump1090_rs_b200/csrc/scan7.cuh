@@ -1,7 +1,7 @@
-// dump1090_rs_b200/csrc/scan7.cuh -- scan kernel v7 (sm_100a): the same stage-1 contract as
-// scan_kernel in kernels.cuh (one thread block per tile -> 24-byte records + ICAO add-events),
-// reorganised so that magnitudes, first differences, correlator signs and edge bits never
-// leave registers between the IQ load and the bit planes.
+// dump1090_rs_b200/csrc/scan7.cuh -- the stage-1 kernel (sm_100a): one thread block per tile of T output
+// positions -> 24-byte records {j, five classified try-phases} of the positions that pass the preamble
+// gates + ICAO add-events.  Magnitudes, first differences, correlator signs and edge bits never leave
+// registers between the IQ load and the bit planes.
 //
 // Dense phase.  The halo-extended tile is NG groups of 192 samples.  Three lanes own a group:
 // lane c (0..2) takes, for slot k = 15..0, the four consecutive samples 192G + 12k + 4c + e
@@ -19,11 +19,19 @@
 //        rising/falling planes (32 positions at stride 12 per word) -> per (rho, word) the match
 //        mask and the template case as three bit planes
 //   P3b  warps expand 32 mask words per round into one (word, bit) list (warp scan + one shared
-//        atomic per round; order is irrelevant because the gates only set survivor bits)
+//        atomic per round; order is irrelevant because the gates only set survivor bits); the list
+//        lives in the edge planes, which are dead by then
 //   P3c  SNR and quiet-zone gates, one match per thread, no branch per template case
 //                                                                    (src/demod_2400.rs:129-146)
-//   P4   one warp scans the survivor bitmap; then, as in v6: field extraction from the planes,
-//        class-staged CRC-24, records, ICAO add-events
+//   P4   one warp scans the survivor bitmap and reserves pool space; all warps list the survivors;
+//        per (survivor, try-phase): five 23-bit field extracts from the planes, DF, items that need a
+//        CRC staged by class; CRC-24 by shuffle-table field sums; record words; ICAO add-events
+//                                                    (src/mode_s/mod.rs:34-139, src/crc.rs:263-282)
+//
+// The kernel is compiled three times: generic (any tile size, lengths, alignment, carry), with the
+// default tile as a template constant (the shared memory plan becomes immediates) and, on top of that,
+// for batches of whole standard buffers.  What was measured and dropped is listed in profiles/README.md;
+// -DB200_SCAN7_STOP / -DB200_ABL give the measurement builds used there.
 #pragma once
 #include "kernels.cuh"
 
@@ -40,9 +48,6 @@ constexpr int k7FieldItems = 5 * k7CandCap;
 constexpr int k7ListCap = 1024;             // template matches gated per round (at most; see Scan7Smem::list_cap)
 #ifndef B200_SCAN7_MIN_BLOCKS
 #define B200_SCAN7_MIN_BLOCKS 7
-#endif
-#ifndef B200_SCAN7_FILL_ALL
-#define B200_SCAN7_FILL_ALL 1               // 1: all warps fill the candidate list (0: warp 0 alone)
 #endif
 #ifndef B200_SCAN7_RING
 #define B200_SCAN7_RING 3                   // IQ rows in flight per lane (cp.async ring)
@@ -255,9 +260,6 @@ __device__ __forceinline__ void gate_eval_bf(const uint16_t *mag, uint32_t *surv
     atomicOr(&surv[jl >> 5], 1u << (jl & 31));
 }
 
-#ifndef B200_SCAN7_P3A_SPLIT
-#define B200_SCAN7_P3A_SPLIT 1              // warps sharing the template pass (1, 2 or 4): static residue ranges
-#endif
 // P3a for the residues RHO0..RHO0+NRHO-1, lane = word column w: the 32 positions 12*(32w+bit)+rho.
 // X[i] is the plane word for edge offset s = i - (rho - RHO0): row t = RHO0 + i mod 12, shifted by
 // one bit when t >= 12 (the carry into the next 12-sample period).  Output per (rho, w): the match
@@ -334,9 +336,7 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     uint16_t *cand = reinterpret_cast<uint16_t *>(smem + P.off_cand);
     const uint32_t *lut = p.lut;
     __shared__ uint32_t s_base, s_count, s_ok, s_nlong, s_nshort;
-#if B200_SCAN7_FILL_ALL
     __shared__ uint16_t s_pair_off[k7Threads];
-#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #if B200_SCAN7_STAGGER
@@ -492,22 +492,8 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
     // and the template case as three bit planes.
     if (tid == 0)
         s_count = 0;
-#if B200_SCAN7_P3A_SPLIT == 1
     if (warp == 0)
         p3a_rows<0, 12>(planes, WP, nwq, lane, masks, P.Wrow);
-#elif B200_SCAN7_P3A_SPLIT == 2
-    if (warp == 0)
-        p3a_rows<0, 6>(planes, WP, nwq, lane, masks, P.Wrow);
-    else if (warp == 1)
-        p3a_rows<6, 6>(planes, WP, nwq, lane, masks, P.Wrow);
-#else
-    switch (warp) {
-    case 0: p3a_rows<0, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
-    case 1: p3a_rows<3, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
-    case 2: p3a_rows<6, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
-    default: p3a_rows<9, 3>(planes, WP, nwq, lane, masks, P.Wrow); break;
-    }
-#endif
     __syncthreads();
     // ---- P3b: expand the match masks into one list (order is irrelevant: the gates only set
     // survivor bits): a warp takes 32 (rho, w) words per round
@@ -605,7 +591,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 incl += t;
         }
         my_off = incl - cnt;
-#if B200_SCAN7_FILL_ALL
         {   // exclusive survivor offset of every pair of words: all warps fill the candidate list
             int o = my_off;
 #pragma unroll
@@ -614,7 +599,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 o += __popc(wv[2 * h2]) + __popc(wv[2 * h2 + 1]);
             }
         }
-#endif
         if (lane == 31) {
             const uint32_t total = (uint32_t)incl;
             uint32_t base = 0, ok = 1;
@@ -646,7 +630,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
         crcl.t[c] = __ldg(p.crc_lanes + 32 * c + lane);
     const unsigned long long ord_buf = (p.ord_first + (unsigned long long)b * p.ord_stride) << 20;
     for (int win = 0; win < C; win += k7CandCap) {
-#if B200_SCAN7_FILL_ALL
         {
             int off = s_pair_off[tid];
 #pragma unroll
@@ -670,22 +653,6 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
                 }
             }
         }
-#else
-        if (warp == 0) {
-            int off = my_off;
-#pragma unroll
-            for (int h = 0; h < 8; h++) {
-                uint32_t wv2 = wv[h];
-                while (wv2) {
-                    const int bit = __ffs(wv2) - 1;
-                    wv2 &= wv2 - 1;
-                    if (off >= win && off < win + k7CandCap)
-                        cand[off - win] = (uint16_t)((8 * lane + h) * 32 + bit);
-                    off++;
-                }
-            }
-        }
-#endif
         __syncthreads();
         const int Cw = min(k7CandCap, C - win);
         uint32_t *rec_w = p.rec + 6ull * (s_base + (uint32_t)win);
