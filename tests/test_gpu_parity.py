@@ -749,3 +749,46 @@ def test_stage1_records_deep_in_a_large_batch(pkg, oracle_mod):
         got = [(int(r[0]), _norm_words([int(x) for x in r[1:]])) for r in rec[sel]]
         ref = [(j, _norm_words(w)) for j, w in o.records(o.to_mag(host[k]), cap=1 << 17)]
         assert got == ref, b
+
+
+@pytest.mark.parametrize("mode", ["lengths", "carry", "unaligned"])
+def test_default_tile_non_standard_batches(mode, pkg, oracle_mod):
+    """The kernel form with the default tile as a compile-time constant but WITHOUT the standard-batch
+    assumptions (>= 33 full-size buffers pick the default tile; per-buffer lengths, carry mode or an
+    unaligned stride rule the standard form out): frames equal the oracle's."""
+    from dump1090_rs_b200 import _ffi, synth
+    nb, spb = 36, 131072
+    batch = synth.make_batch(91, nb, msgs_per_buffer=12, icao_pool=6)
+    c = pkg.Context(0)
+    if mode == "lengths":
+        rng = np.random.default_rng(5)
+        lens = [int(x) for x in rng.integers(90000, spb + 1, nb)]
+        lens[3], lens[17] = spb, 7384 * 17 + 5           # a full one, and one whose last tile is 5 positions
+        ref, o = oracle_stream(oracle_mod, [batch[b, :lens[b]] for b in range(nb)])
+        got = c.demod_iq_batch(batch, nb, spb, lengths=lens)
+    elif mode == "carry":
+        c.set_option(_ffi.OPT_CARRY, 1)
+        o = oracle_mod.Oracle()
+        ref = []
+        for b in range(nb):
+            for f in o.demod_iq_carry(batch[b]):
+                f["buffer"] = b
+                ref.append(f)
+        got = c.demod_iq_batch(batch, nb, spb)
+    else:
+        stride = spb + 2                                   # stride % 4 != 0: scalar loads
+        wide = np.zeros((nb, stride, 2), dtype=np.int16)
+        wide[:, :spb] = batch
+        ref, o = oracle_stream(oracle_mod, [batch[b] for b in range(nb)])
+        import torch
+        d = torch.from_numpy(wide).to("cuda:0")
+        out = torch.zeros((8192, 28), dtype=torch.uint8, device="cuda:0")
+        n = c.demod_iq_batch_ptr(d.data_ptr(), nb, spb, stride, out.data_ptr(), 8192)
+        raw = out[:n].cpu().numpy()
+        got = [dict(buffer=int(r[24:28].view(np.uint32)[0]), j=int(r[20:24].view(np.uint32)[0]), phase=int(r[15]),
+                    score=int(r[16:18].view(np.int16)[0]), msg=bytes(r[: r[14]])) for r in raw]
+    assert len(ref) > 100
+    assert frames_key(got) == frames_key(ref), mode
+    if mode != "carry":
+        assert set(c.icao_snapshot()) == o.members()
+    c.close()
