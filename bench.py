@@ -88,7 +88,8 @@ class ClockSampler:
     def _poll_nvml(self):
         nv = self._nv
         self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
-        self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        if not self.mx:          # a constant of the board: one query
+            self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)))
         try:
             bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
         except Exception:
@@ -117,7 +118,8 @@ class ClockSampler:
                     self._poll_smi()
             except Exception:
                 pass
-            self._stop.wait(0.0005 if self._h is not None else 0.1)
+            if self._h is None:
+                self._stop.wait(0.1)          # (NVML polls back to back: the timed region is milliseconds)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
