@@ -546,6 +546,35 @@ def main() -> int:
                               "gbytes_per_s_per_gpu": nb * SAMPLES * 4 * k_e2e / dt_copy / 1e9,
                               "e2e_fraction_of_ceiling": dt_copy / dt, "numa": numa,
                               "what": "the same pinned host batch through cudaMemcpyAsync alone (max over ranks)"}
+        if not args.no_sub:
+            # opt-in 8-bit ingest (RTL-SDR delivers u8; the reference receives SoapySDR's CS16 expansion of it):
+            # the same batch as u8 pairs, expanded on the device -- half the bytes over PCIe, identical frames
+            L = _ffi.lib()
+            lut = torch.tensor([L.b200adsb_cu8_to_cs16(v) for v in range(256)], dtype=torch.int16, device=dev)
+            inv = torch.zeros(65536, dtype=torch.uint8, device=dev)
+            inv[lut.to(torch.int64) + 32768] = torch.arange(256, dtype=torch.uint8, device=dev)
+            host_u8 = torch.empty((nb, SAMPLES, 2), dtype=torch.uint8, pin_memory=True)
+            host_u8.copy_(inv[iq.to(torch.int64) + 32768])
+            ectx.icao_flush()
+            nf8 = ectx.demod_cu8_batch_ptr(host_u8.data_ptr(), nb, SAMPLES, SAMPLES, host_frames.data_ptr(), cap)
+            barrier()
+            t2 = time.perf_counter()
+            for _ in range(k_e2e):
+                ectx.icao_flush()
+                nf8 = ectx.demod_cu8_batch_ptr(host_u8.data_ptr(), nb, SAMPLES, SAMPLES, host_frames.data_ptr(), cap)
+            torch.cuda.synchronize()
+            dt8 = time.perf_counter() - t2
+            if dist is not None:
+                t = torch.tensor([dt8], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt8 = float(t.item())
+            sub["e2e_cu8_ingest"] = {"value": total_samples * k_e2e / dt8 / 1e6, "unit": UNIT,
+                                     "h2d_bytes_per_step": nb * SAMPLES * 2, "frames_per_step": nf8,
+                                     "same_frames_as_cs16": nf8 == nf,
+                                     "what": "opt-in b200adsb_demod_cu8_batch: the batch as unsigned 8-bit pairs (what an RTL-SDR "
+                                             "delivers), expanded to CS16 on the device with SoapySDR's conversion; NOT the "
+                                             "headline e2e, which moves the reference's CS16"}
+            del host_u8
         ectx.close()
         del host_iq, stage
 

@@ -95,6 +95,10 @@ _PROTOS = {
     "b200adsb_demod_iq_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                           C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                           C.c_void_p]),
+    "b200adsb_demod_cu8_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                           C.c_void_p]),
+    "b200adsb_cu8_to_cs16": (C.c_int16, [C.c_uint8]),
     "b200adsb_demod_iq_batch_dev_async": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,
                                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200adsb_demod_iq_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t,

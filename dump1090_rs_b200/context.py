@@ -121,6 +121,22 @@ class Context:
         fr = self._frames(out, n.value)
         return (fr, cnt[:n_buffers]) if want_counts else fr
 
+    def demod_cu8_batch(self, iq_u8, n_buffers: int, samples_per_buffer: int, cap: int = 1 << 16):
+        """Opt-in 8-bit ingest (b200adsb_demod_cu8_batch): uint8 (I, Q) pairs, expanded to CS16 on the device."""
+        a = np.ascontiguousarray(iq_u8, dtype=np.uint8).reshape(-1)
+        out = (Frame * cap)()
+        n = C.c_size_t(0)
+        self._check(self._L.b200adsb_demod_cu8_batch(self._h, a.ctypes.data, n_buffers, samples_per_buffer,
+                                                     samples_per_buffer, None, out, cap, C.byref(n), None),
+                    "demod_cu8_batch")
+        return self._frames(out, n.value)
+
+    def demod_cu8_batch_ptr(self, iq_ptr: int, n_buffers: int, spb: int, stride: int, out_ptr: int, cap: int) -> int:
+        n = C.c_size_t(0)
+        self._check(self._L.b200adsb_demod_cu8_batch(self._h, iq_ptr, n_buffers, spb, stride, None, out_ptr, cap,
+                                                     C.byref(n), None), "demod_cu8_batch")
+        return int(n.value)
+
     # raw-pointer forms (device memory owned by the caller, e.g. torch tensors)
     def demod_iq_batch_ptr(self, iq_ptr: int, n_buffers: int, spb: int, stride: int, out_ptr: int,
                            cap: int, lengths_ptr: int = 0, counts_ptr: int = 0, host: bool = False) -> int:

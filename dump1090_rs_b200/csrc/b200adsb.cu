@@ -69,6 +69,8 @@ struct b200adsb_ctx {
 
     void *d_stage = nullptr;
     size_t stage_bytes = 0;
+    uint8_t *d_stage8 = nullptr;      // CU8 ingest: the 8-bit samples as they crossed PCIe
+    size_t stage8_bytes = 0;
     b200adsb_frame *d_frames = nullptr;
     size_t frames_cap = 0;
     uint32_t *d_counts = nullptr;
@@ -766,6 +768,7 @@ void b200adsb_ctx_destroy(b200adsb_ctx *c)
         if (sl.done) cudaEventDestroy(sl.done);
     }
     cudaFree(c->d_stage);
+    cudaFree(c->d_stage8);
     cudaFree(c->d_frames);
     cudaFree(c->d_counts);
     cudaFree(c->d_lengths);
@@ -1114,11 +1117,15 @@ int b200adsb_demod_iq_batch_dev(b200adsb_ctx *c, const int16_t *d_iq, size_t n_b
 }
 
 // ------------------------------------------------------------------ host batch
-int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers, size_t spb,
-                            size_t stride, const uint32_t *lengths, b200adsb_frame *out, size_t cap,
-                            size_t *n_out, uint32_t *per_buffer_counts)
+}  // extern "C"
+namespace {
+// iq8 != nullptr: the source is 8-bit unsigned (I, Q) pairs (RTL-SDR native); they cross PCIe as they are
+// (2 bytes per sample) and are expanded to CS16 on the device by cu8_expand_kernel
+int host_batch(b200adsb_ctx *c, const int16_t *iq, const uint8_t *iq8, size_t n_buffers, size_t spb,
+               size_t stride, const uint32_t *lengths, b200adsb_frame *out, size_t cap,
+               size_t *n_out, uint32_t *per_buffer_counts)
 {
-    if (!c || (!iq && n_buffers && spb) || (!out && cap))
+    if (!c || (!iq && !iq8 && n_buffers && spb) || (!out && cap))
         return B200ADSB_ERR_BAD_ARG;
     if (spb > (size_t)kMaxSamples || (stride < spb && n_buffers > 1))
         return B200ADSB_ERR_BAD_ARG;
@@ -1136,6 +1143,10 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers
         rc = ensure_stage(c, std::max<size_t>(nb * dstride * 4, 16));
         if (rc) return rc;
         int16_t *d_iq = reinterpret_cast<int16_t *>(c->d_stage);
+        if (iq8) {
+            rc = grow(c, &c->d_stage8, &c->stage8_bytes, std::max<size_t>(nb * dstride * 2, 16));
+            if (rc) return rc;
+        }
         const uint32_t *d_len = nullptr;
         if (lengths) {
             rc = grow(c, &c->d_lengths, &c->lengths_cap, nb);
@@ -1166,7 +1177,15 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers
         for (size_t k = 0; k < n_chunks; k++) {
             const size_t b0 = k * chunk, cb = std::min(chunk, nb - b0);
             const int16_t *src = iq + 2 * (done + b0) * stride;
-            if (spb) {
+            if (spb && iq8) {
+                uint8_t *d8 = c->d_stage8 + 2 * b0 * dstride;
+                const uint8_t *src8 = iq8 + 2 * (done + b0) * stride;
+                if (stride == dstride)
+                    CK(c, cudaMemcpyAsync(d8, src8, cb * dstride * 2, cudaMemcpyHostToDevice, c->copy_stream));
+                else
+                    CK(c, cudaMemcpy2DAsync(d8, dstride * 2, src8, stride * 2, spb * 2, cb, cudaMemcpyHostToDevice,
+                                            c->copy_stream));
+            } else if (spb) {
                 if (stride == dstride) {
                     CK(c, cudaMemcpyAsync(d_iq + 2 * b0 * dstride, src, cb * dstride * 4, cudaMemcpyHostToDevice, c->copy_stream));
                 } else {
@@ -1176,6 +1195,14 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers
             }
             CK(c, cudaEventRecord(c->chunk_events[k], c->copy_stream));
             CK(c, cudaStreamWaitEvent(c->stream, c->chunk_events[k], 0));
+            if (spb && iq8) {
+                const size_t words = cb * dstride / 2;     // 4 bytes = two samples per thread; dstride % 4 == 0
+                cu8_expand_kernel<<<(unsigned)((words + 255) / 256), 256, 0, c->stream>>>(
+                    reinterpret_cast<const uint32_t *>(c->d_stage8 + 2 * b0 * dstride),
+                    reinterpret_cast<uint2 *>(d_iq + 2 * b0 * dstride), words);
+                CK(c, cudaGetLastError());
+                c->timing.other_launches++;
+            }
             rc = launch_scan(c, (uint32_t)b0, (uint32_t)cb);
             if (rc) { c->cur.active = false; return rc; }
         }
@@ -1202,6 +1229,29 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers
     if (n_out)
         *n_out = total_frames;
     return status;
+}
+}  // namespace
+extern "C" {
+
+int b200adsb_demod_iq_batch(b200adsb_ctx *c, const int16_t *iq, size_t n_buffers, size_t spb,
+                            size_t stride, const uint32_t *lengths, b200adsb_frame *out, size_t cap,
+                            size_t *n_out, uint32_t *per_buffer_counts)
+{
+    return host_batch(c, iq, nullptr, n_buffers, spb, stride, lengths, out, cap, n_out, per_buffer_counts);
+}
+
+int b200adsb_demod_cu8_batch(b200adsb_ctx *c, const uint8_t *iq_u8, size_t n_buffers, size_t spb,
+                             size_t stride, const uint32_t *lengths, b200adsb_frame *out, size_t cap,
+                             size_t *n_out, uint32_t *per_buffer_counts)
+{
+    if (!iq_u8 && n_buffers && spb)
+        return B200ADSB_ERR_BAD_ARG;
+    return host_batch(c, nullptr, iq_u8, n_buffers, spb, stride, lengths, out, cap, n_out, per_buffer_counts);
+}
+
+int16_t b200adsb_cu8_to_cs16(uint8_t v)
+{
+    return (int16_t)((((float)v - 127.4f) * (1.0f / 128.0f)) * 32767.0f);
 }
 
 // ------------------------------------------------------------------ receive loop (double buffered)

@@ -515,6 +515,24 @@ __global__ void mag_sweep_kernel(unsigned long long *mismatches, uint32_t *first
         atomicAdd(mismatches, (unsigned long long)bad);
 }
 
+// CU8 ingest: 8-bit unsigned (I, Q) pairs -> CS16 with the conversion SoapySDR's RTL-SDR module applies when
+// asked for CS16 (the reference's default driver, dump1090_rs/src/main.rs:49-55,143):
+//   int16((float(u8) - 127.4f) * (1.0f / 128.0f) * 32767.0f), truncating.  Two samples per thread.
+__device__ __forceinline__ uint32_t cu8_to_cs16(uint32_t v)
+{
+    const float f = __fmul_rn(__fmul_rn(__fsub_rn(__uint2float_rn(v), 127.4f), 1.0f / 128.0f), 32767.0f);
+    return (uint32_t)__float2int_rz(f) & 0xffffu;
+}
+__global__ void cu8_expand_kernel(const uint32_t *__restrict__ in, uint2 *__restrict__ out, size_t words)
+{
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= words)
+        return;
+    const uint32_t w = __ldg(in + i);       // I0 Q0 I1 Q1
+    out[i] = make_uint2(cu8_to_cs16(w & 0xffu) | (cu8_to_cs16((w >> 8) & 0xffu) << 16),
+                        cu8_to_cs16((w >> 16) & 0xffu) | (cu8_to_cs16(w >> 24) << 16));
+}
+
 // ================================================================== message-level kernels
 __global__ void checksum_kernel(const uint8_t *__restrict__ msgs, int n, int nbytes,
                                 const uint32_t *__restrict__ tab256, uint32_t *__restrict__ out)

@@ -138,6 +138,16 @@ int b200adsb_demod_iq_batch(b200adsb_ctx *ctx, const int16_t *iq_re_im, size_t n
                             const uint32_t *lengths, b200adsb_frame *out, size_t cap,
                             size_t *n_out, uint32_t *per_buffer_counts);
 
+/* Opt-in ingest for 8-bit front ends (RTL-SDR, the reference's default --driver): the same call on unsigned
+ * 8-bit (I, Q) pairs as the radio delivers them.  They cross PCIe as 2 bytes per sample and are expanded on
+ * the device with the conversion SoapySDR's RTL-SDR module applies when the reference asks it for CS16
+ * (main.rs:143): int16((float(u8) - 127.4f) * (1.0f / 128.0f) * 32767.0f) -- b200adsb_cu8_to_cs16 is that
+ * function on the host -- so the frames are those of b200adsb_demod_iq_batch on the converted samples. */
+int b200adsb_demod_cu8_batch(b200adsb_ctx *ctx, const uint8_t *iq_u8, size_t n_buffers,
+                             size_t samples_per_buffer, size_t stride_samples, const uint32_t *lengths,
+                             b200adsb_frame *out, size_t cap, size_t *n_out, uint32_t *per_buffer_counts);
+int16_t b200adsb_cu8_to_cs16(uint8_t v);
+
 /* Same with the IQ already resident in device memory (d_iq) and frames left in
  * device memory (d_out, cap entries); *n_out is read back.  d_lengths nullable
  * (device).  d_per_buffer_counts nullable (device, n_buffers u32). */

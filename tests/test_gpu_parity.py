@@ -792,3 +792,33 @@ def test_default_tile_non_standard_batches(mode, pkg, oracle_mod):
     if mode != "carry":
         assert set(c.icao_snapshot()) == o.members()
     c.close()
+
+
+def test_cu8_ingest_equals_cs16_path(pkg, oracle_mod):
+    """Opt-in 8-bit ingest (b200adsb_demod_cu8_batch): unsigned 8-bit (I, Q) pairs expanded to CS16 on the
+    device give the frames of the CS16 path -- and of the oracle -- on the host-converted samples; ragged
+    stride and more buffers than one H2D chunk."""
+    import ctypes as C
+    from dump1090_rs_b200 import _ffi, synth
+    L = _ffi.lib()
+    lut = np.array([L.b200adsb_cu8_to_cs16(v) for v in range(256)], dtype=np.int16)
+    nb, spb = 5, 131072
+    cs16 = synth.make_batch(33, nb, msgs_per_buffer=30, icao_pool=5)
+    inv = {int(v): k for k, v in enumerate(lut)}
+    u8 = np.vectorize(inv.__getitem__, otypes=[np.uint8])(cs16)      # synth samples are table values
+    assert (lut[u8] == cs16).all()
+    ref, o = oracle_stream(oracle_mod, [cs16[b] for b in range(nb)])
+    assert len(ref) > 50
+    c = pkg.Context(0)
+    c.set_option(_ffi.OPT_H2D_CHUNK, 2)
+    assert frames_key(c.demod_cu8_batch(u8, nb, spb)) == frames_key(ref)
+    assert set(c.icao_snapshot()) == o.members()
+    c.icao_flush()
+    assert frames_key(c.demod_iq_batch(cs16, nb, spb)) == frames_key(ref)
+    # ragged: 50,001-sample buffers (device stride rounded up to 4 samples)
+    c.icao_flush()
+    spb2 = 50001
+    cut16 = np.ascontiguousarray(cs16[:, :spb2])
+    ref2, _ = oracle_stream(oracle_mod, [cut16[b] for b in range(nb)])
+    assert frames_key(c.demod_cu8_batch(np.ascontiguousarray(u8[:, :spb2]), nb, spb2)) == frames_key(ref2)
+    c.close()

@@ -3,6 +3,8 @@ closed-form bit positions, difference form of the correlators, edge-bit form of 
 templates, and the CRC-24 field tables.  No GPU needed."""
 import ctypes as C
 
+import os
+
 import numpy as np
 import pytest
 
@@ -145,6 +147,20 @@ def test_crc_lane_tables(oracle_mod):
             s = _mulx(s) ^ a56(f[r])
         s ^= (f[0] >> 11) & 1
         assert s == oracle_mod.modes_checksum(m[:7], 56)
+
+
+def test_cu8_conversion_table():
+    """b200adsb_cu8_to_cs16 (the device's cu8_expand_kernel uses the same f32 expression): SoapySDR's RTL-SDR
+    u8 -> CS16 conversion, which is also the mapping that reproduces the value set of the reference's captures
+    (..., -358, -102, 153, 409, ...)."""
+    L = _ffi.lib()
+    lut = np.array([L.b200adsb_cu8_to_cs16(v) for v in range(256)], dtype=np.int16)
+    f32 = (((np.arange(256, dtype=np.float32) - np.float32(127.4)) * np.float32(1.0 / 128.0)) * np.float32(32767.0)).astype(np.int16)
+    assert (lut == f32).all()
+    assert {-358, -102, 153, 409} <= set(int(x) for x in lut)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "captures.npz"))
+    for k in z.files:                         # every sample of the captures is a table value
+        assert np.isin(np.unique(z[k]), lut).all(), k
 
 
 def test_abi_exports_match_header():
