@@ -118,8 +118,7 @@ class ClockSampler:
                     self._poll_smi()
             except Exception:
                 pass
-            if self._h is None:
-                self._stop.wait(0.1)          # (NVML polls back to back: the timed region is milliseconds)
+            self._stop.wait(0.0005 if self._h is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
