@@ -709,7 +709,7 @@ def main() -> int:
                        "step_call": ("synchronous ABI calls (host round trips inside every step)" if not queued_steps else
                                      ("b200adsb_demod_iq_batch_dev_async" if world == 1 else
                                       "b200adsb_scan_batch_dev_async + event exchange (" + sh.exchange + ") + "
-                                      "b200adsb_resolve_batch_dev_async + frames pack / all-gather / merge on a side stream")
+                                      "b200adsb_resolve_batch_dev_async + frame gather (" + sh.exchange + ") on a side stream")
                                      + " (steps queued back to back, outcomes checked after the timed region)")},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "parity_on_sample": None if parity is None else parity["ok"], "parity": parity,

@@ -126,6 +126,11 @@ _PROTOS = {
                                            C.c_size_t]),
     "b200adsb_frames_merge_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                             C.c_size_t, C.c_void_p]),
+    "b200adsb_frames_symm_bytes": (C.c_size_t, [C.c_size_t, C.c_size_t]),
+    "b200adsb_frames_push_symm_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64, C.c_void_p]),
+    "b200adsb_frames_merge_symm_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint64,
+                                                 C.c_void_p, C.c_size_t, C.c_void_p]),
     "b200adsb_resolve_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
                                              C.c_void_p]),
     "b200adsb_icao_flush": (C.c_int, [C.c_void_p]),

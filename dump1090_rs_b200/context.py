@@ -209,6 +209,17 @@ class Context:
         self._check(self._L.b200adsb_frames_merge_dev(self._h, stream or None, gathered_ptr, n_ranks, rows_cap,
                                                       out_ptr or None, cap, n_out_ptr), "frames_merge")
 
+    def frames_push_symm_dev(self, frames_ptr: int, peer_bufs_dev_ptr: int, rank: int, n_ranks: int, rows_cap: int,
+                             epoch: int, ticket_ptr: int, count: int = 0, count_ptr: int = 0, stream: int = 0):
+        self._check(self._L.b200adsb_frames_push_symm_dev(self._h, stream or None, frames_ptr or None,
+                                                          count_ptr or None, count, peer_bufs_dev_ptr, rank, n_ranks,
+                                                          rows_cap, epoch, ticket_ptr), "frames_push_symm")
+
+    def frames_merge_symm_dev(self, local_buf_ptr: int, n_ranks: int, rows_cap: int, epoch: int, out_ptr: int, cap: int,
+                              n_out_ptr: int, stream: int = 0):
+        self._check(self._L.b200adsb_frames_merge_symm_dev(self._h, stream or None, local_buf_ptr, n_ranks, rows_cap,
+                                                           epoch, out_ptr or None, cap, n_out_ptr), "frames_merge_symm")
+
     def resolve_batch_dev(self, out_ptr: int, cap: int, counts_ptr: int = 0) -> int:
         n = C.c_size_t(0)
         self._check(self._L.b200adsb_resolve_batch_dev(self._h, out_ptr, cap, C.byref(n), counts_ptr or None),

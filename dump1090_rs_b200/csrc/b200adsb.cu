@@ -1056,7 +1056,52 @@ int b200adsb_frames_merge_dev(b200adsb_ctx *c, void *stream, const b200adsb_fram
     int rc = bind(c);
     if (rc) return rc;
     frames_merge_kernel<<<16, 256, 0, st>>>(d_gathered, (uint32_t)n_ranks, (uint32_t)rows_cap, d_out,
-                                                   (uint32_t)std::min<size_t>(cap, 0xffffffffu), d_n_out);
+                                                   (uint32_t)std::min<size_t>(cap, 0xffffffffu), d_n_out, nullptr, 0ull);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+size_t b200adsb_frames_symm_bytes(size_t n_ranks, size_t rows_cap)
+{
+    return 16 * n_ranks + 2 * n_ranks * (rows_cap + 1) * sizeof(b200adsb_frame);
+}
+
+int b200adsb_frames_push_symm_dev(b200adsb_ctx *c, void *stream, const b200adsb_frame *d_frames,
+                                  const uint32_t *d_count, size_t count, void *const *d_peer_bufs, size_t rank,
+                                  size_t n_ranks, size_t rows_cap, uint64_t epoch, uint32_t *d_ticket)
+{
+    if (!c || !d_peer_bufs || !d_ticket || n_ranks == 0 || n_ranks > 256 || rank >= n_ranks || rows_cap == 0 ||
+        rows_cap > 0xfffffffeu || epoch == 0 || (!d_frames && (d_count || count)))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    frames_push_symm_kernel<<<8, 256, 0, st>>>(d_frames, d_count, (uint32_t)std::min<size_t>(count, 0xffffffffu),
+                                               (unsigned char *const *)d_peer_bufs, (uint32_t)rank, (uint32_t)n_ranks,
+                                               (uint32_t)rows_cap, epoch, d_ticket);
+    CK(c, cudaGetLastError());
+    c->timing.other_launches++;
+    return B200ADSB_OK;
+}
+
+int b200adsb_frames_merge_symm_dev(b200adsb_ctx *c, void *stream, void *d_local_buf, size_t n_ranks,
+                                   size_t rows_cap, uint64_t epoch, b200adsb_frame *d_out, size_t cap,
+                                   uint32_t *d_n_out)
+{
+    if (!c || !d_local_buf || !d_n_out || n_ranks == 0 || n_ranks > 256 || rows_cap == 0 || rows_cap > 0xfffffffeu ||
+        epoch == 0 || (!d_out && cap))
+        return B200ADSB_ERR_BAD_ARG;
+    int rc = bind(c);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    const uint32_t parity = (uint32_t)(epoch & 1);
+    unsigned char *base = reinterpret_cast<unsigned char *>(d_local_buf);
+    const b200adsb_frame *blocks = reinterpret_cast<const b200adsb_frame *>(base + 16 * n_ranks) +
+                                   (size_t)parity * n_ranks * (rows_cap + 1);
+    const unsigned long long *flags = reinterpret_cast<const unsigned long long *>(base) + (size_t)parity * n_ranks;
+    frames_merge_kernel<<<16, 256, 0, st>>>(blocks, (uint32_t)n_ranks, (uint32_t)rows_cap, d_out,
+                                            (uint32_t)std::min<size_t>(cap, 0xffffffffu), d_n_out, flags, epoch);
     CK(c, cudaGetLastError());
     c->timing.other_launches++;
     return B200ADSB_OK;

@@ -1394,6 +1394,54 @@ __global__ void frames_pack_kernel(const b200adsb_frame *frames, const uint32_t 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 7u * m; i += gridDim.x * blockDim.x)
         dst[i] = src[i];
 }
+// The same gather fused with its transport, like the event exchange above: every rank owns
+//   u64 flags[2][world]   then   frame blocks[2][world][1 + rows_cap]
+// in symmetric memory; frames_push_symm_kernel stores this rank's block into slot [parity][rank] of every
+// rank's buffer over NVLink and the last block to finish raises the rank's flag everywhere;
+// frames_merge_kernel, given the local flags and the epoch, waits for all of them before it merges.
+__device__ __forceinline__ b200adsb_frame *symm_frames(unsigned char *base, uint32_t world, uint32_t rows_cap,
+                                                       uint32_t parity, uint32_t r)
+{
+    return reinterpret_cast<b200adsb_frame *>(base + 16ull * world) +
+           ((unsigned long long)parity * world + r) * ((unsigned long long)rows_cap + 1);
+}
+__global__ void frames_push_symm_kernel(const b200adsb_frame *frames, const uint32_t *d_count, uint32_t count,
+                                        unsigned char *const *peer_bufs, uint32_t rank, uint32_t world,
+                                        uint32_t rows_cap, unsigned long long epoch, uint32_t *ticket)
+{
+    __shared__ uint32_t s_last;
+    const uint32_t parity = (uint32_t)(epoch & 1ull);
+    const uint32_t n = d_count ? *d_count : count;
+    const uint32_t m = min(n, rows_cap);
+    if (blockIdx.x == 0 && threadIdx.x < world) {
+        uint32_t *h = reinterpret_cast<uint32_t *>(symm_frames(peer_bufs[threadIdx.x], world, rows_cap, parity, rank));
+        h[0] = n;
+        for (int k = 1; k < 7; k++)
+            h[k] = 0;
+    }
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(frames);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < 7u * m; i += gridDim.x * blockDim.x) {
+        const uint32_t v = src[i];
+        for (uint32_t q = 0; q < world; q++)
+            reinterpret_cast<uint32_t *>(symm_frames(peer_bufs[q], world, rows_cap, parity, rank) + 1)[i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if (threadIdx.x < world) {
+            unsigned long long *flag =
+                reinterpret_cast<unsigned long long *>(peer_bufs[threadIdx.x]) + (unsigned long long)parity * world + rank;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(epoch) : "memory");
+        }
+        if (threadIdx.x == 0)
+            *ticket = 0;
+    }
+}
+
 __device__ __forceinline__ unsigned long long frame_key(const b200adsb_frame *f, uint32_t rank, uint32_t world)
 {
     return ((unsigned long long)(f->buffer * world + rank) << 32) | f->j;   // round-robin dealing: g = local * world + rank
@@ -1402,9 +1450,40 @@ __device__ __forceinline__ unsigned long long frame_key(const b200adsb_frame *f,
 // buffer indices.  A frame's slot = its index in its own list + the number of frames with a smaller key in
 // every other list (binary search; keys of different ranks never tie: they are different buffers).
 // n_out[0] = total frames, n_out[1] = 1 if a rank had more frames than rows_cap or the total exceeds cap.
+// wait_flags != nullptr: the blocks arrive by peer stores; wait (bounded, ~30 s) until the n_ranks flags have
+// reached `epoch`.  A peer that never arrives sets n_out[1] = 3.
 __global__ void frames_merge_kernel(const b200adsb_frame *gathered, uint32_t n_ranks, uint32_t rows_cap,
-                                    b200adsb_frame *out, uint32_t cap, uint32_t *n_out)
+                                    b200adsb_frame *out, uint32_t cap, uint32_t *n_out,
+                                    const unsigned long long *wait_flags, unsigned long long epoch)
 {
+    if (wait_flags) {
+        __shared__ uint32_t s_timeout;
+        if (threadIdx.x == 0)
+            s_timeout = 0;
+        __syncthreads();
+        if (threadIdx.x < n_ranks) {
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned long long v;
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+                if (v >= epoch)
+                    break;
+                if (clock64() - t0 > 60000000000ll) {
+                    s_timeout = 1;
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        if (s_timeout) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                n_out[0] = 0;
+                n_out[1] = 3;
+            }
+            return;
+        }
+    }
     const size_t stride = (size_t)rows_cap + 1;
     uint32_t total = 0, ovf = 0;
     for (uint32_t r = 0; r < n_ranks; r++) {

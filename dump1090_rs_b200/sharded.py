@@ -119,6 +119,16 @@ class ShardedDemodulator:
         torch.cuda.synchronize(dev)
         self.symm_hdl = symm_mem.rendezvous(self.symm, g)
         self.peer_bufs_dev = int(self.symm_hdl.buffer_ptrs_dev)
+        # the frame gather's blocks, the same way
+        fbytes = int(_ffi.lib().b200adsb_frames_symm_bytes(self.world, self.frame_rows))
+        self.fsymm = symm_mem.empty((fbytes + 7) // 8, dtype=torch.int64, device=dev)
+        self.fsymm.zero_()
+        torch.cuda.synchronize(dev)
+        self.fsymm_hdl = symm_mem.rendezvous(self.fsymm, g)
+        self.fpeer_bufs_dev = int(self.fsymm_hdl.buffer_ptrs_dev)
+        self.fticket = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.ev_merged = [torch.cuda.Event(), torch.cuda.Event()]
+        self.fepoch = 0
         dist.barrier(group=group)       # nobody pushes before every buffer is zeroed
 
     def _exchange_events(self, poisoned: bool = False) -> None:
@@ -127,6 +137,11 @@ class ShardedDemodulator:
         if self.world <= 1:
             return
         if self.exchange == "symm":
+            # the frame blocks alternate between two parities: the gather that follows this batch reuses the
+            # blocks of the gather before last, so this rank's merge of that one has to be through before its
+            # peers can get past this exchange (they cannot push frames of this batch before they have its events)
+            import torch
+            torch.cuda.current_stream().wait_event(self.ev_merged[(self.fepoch + 1) & 1])
             self.epoch += 1
             self.ctx.events_push_symm_dev(self.peer_bufs_dev, self.rank, self.world, self.event_rows, self.epoch,
                                           force_flags=2 if poisoned else 0)
@@ -202,6 +217,19 @@ class ShardedDemodulator:
         self.ev_resolved.record(main)
         self.fstream.wait_event(self.ev_resolved)
         fs = self.fstream.cuda_stream
+        if self.world > 1 and self.exchange == "symm":
+            # peer stores into every rank's block + flag, then a merge that waits for the flags: no collective
+            # library kernel competes with the next scan for the SMs
+            self.fepoch += 1
+            self.ctx.frames_push_symm_dev(frames_ptr, self.fpeer_bufs_dev, self.rank, self.world, self.frame_rows,
+                                          self.fepoch, self.fticket.data_ptr(), count=count, count_ptr=result_ptr,
+                                          stream=fs)
+            self.ev_packed.record(self.fstream)
+            main.wait_event(self.ev_packed)
+            self.ctx.frames_merge_symm_dev(self.fsymm.data_ptr(), self.world, self.frame_rows, self.fepoch, out_ptr, cap,
+                                           self.n_out.data_ptr(), stream=fs)
+            self.ev_merged[self.fepoch & 1].record(self.fstream)
+            return self.n_out
         self.ctx.frames_pack_dev(frames_ptr, self.fblock.data_ptr(), self.frame_rows, count=count, count_ptr=result_ptr,
                                  stream=fs)
         self.ev_packed.record(self.fstream)

@@ -240,6 +240,21 @@ int b200adsb_frames_pack_dev(b200adsb_ctx *ctx, void *stream, const b200adsb_fra
 int b200adsb_frames_merge_dev(b200adsb_ctx *ctx, void *stream, const b200adsb_frame *d_gathered, size_t n_ranks,
                               size_t rows_cap, b200adsb_frame *d_out, size_t cap, uint32_t *d_n_out);
 
+/* The gather fused with its transport (as b200adsb_events_push/import_symm_dev): every rank owns
+ * b200adsb_frames_symm_bytes(n_ranks, rows_cap) bytes of zero-initialised symmetric memory; push stores this
+ * rank's block into every rank's buffer over NVLink and raises its flag, merge waits (on the device,
+ * bounded) for all flags of the epoch (1, 2, 3, ... one per gather, identical on all ranks) and writes the
+ * ordered stream; d_n_out[1] = 3 when a peer never arrived.  d_ticket: one zeroed device word per caller.
+ * A rank must not start the event exchange of the batch whose gather has epoch e before its own merge of
+ * epoch e - 2 has finished (the blocks alternate between two parities); sharded.py orders that with events. */
+size_t b200adsb_frames_symm_bytes(size_t n_ranks, size_t rows_cap);
+int b200adsb_frames_push_symm_dev(b200adsb_ctx *ctx, void *stream, const b200adsb_frame *d_frames,
+                                  const uint32_t *d_count, size_t count, void *const *d_peer_bufs, size_t rank,
+                                  size_t n_ranks, size_t rows_cap, uint64_t epoch, uint32_t *d_ticket);
+int b200adsb_frames_merge_symm_dev(b200adsb_ctx *ctx, void *stream, void *d_local_buf, size_t n_ranks,
+                                   size_t rows_cap, uint64_t epoch, b200adsb_frame *d_out, size_t cap,
+                                   uint32_t *d_n_out);
+
 /* enqueue-only forms (no host round trip; outcome in d_result as for
  * b200adsb_demod_iq_batch_dev_async): scan_async -> events_pack -> all-gather ->
  * events_import_packed -> resolve_async, all on the context's stream */
