@@ -660,16 +660,17 @@ __global__ void __launch_bounds__(k7Threads, B200_SCAN7_MIN_BLOCKS) scan7_kernel
             const int ci = item / 5, tt = item - 5 * ci;
             const int jl = cand[ci];
             // demod_2400.rs:158-160: P0 = 5*(mi+19) + try_phase, try_phase = 4+tt
-            const int A = jl + kHaloFront + 19;
-            const int qA = A / 12, rA = A - 12 * qA;
-            const uint32_t *lrow = lut + 25 * rA + 5 * tt;
+            const uint32_t A = (uint32_t)(jl + kHaloFront + 19);
+            const uint32_t qA = A / 12u, rA = A - 12u * qA;
+            const uint32_t *lrow = lut + (25u * rA + 5u * (uint32_t)tt);      // (unsigned: one IMAD.WIDE, no sign extension)
             uint32_t f[5];
 #pragma unroll
             for (int r = 0; r < 5; r++) {
                 const uint32_t e = __ldg(lrow + r);
-                const int q = qA + (int)(e >> 16);
+                const uint32_t q = qA + (e >> 16);
                 const uint32_t *stp = planes + (e & 0xffffu) + (q >> 5);
-                f[r] = __funnelshift_r(stp[0], stp[1], q & 31) & (r < 2 ? 0x7fffffu : 0x3fffffu);
+                // (the funnel shift takes its amount modulo 32)
+                f[r] = __funnelshift_r(stp[0], stp[1], q) & (r < 2 ? 0x7fffffu : 0x3fffffu);
             }
             if (tt == 0)
                 rec_w[6 * ci] = (uint32_t)(tile_start + jl);
