@@ -139,7 +139,9 @@ class ShardedDemodulator:
         if self.exchange == "symm":
             # the frame blocks alternate between two parities: the gather that follows this batch reuses the
             # blocks of the gather before last, so this rank's merge of that one has to be through before its
-            # peers can get past this exchange (they cannot push frames of this batch before they have its events)
+            # peers can get past this exchange (they cannot push frames of this batch before they have its events).
+            # With one gather per batch the in-order side streams already guarantee it
+            # (tests/test_exchange_protocol.py); the wait also covers callers that gather only some batches.
             import torch
             torch.cuda.current_stream().wait_event(self.ev_merged[(self.fepoch + 1) & 1])
             self.epoch += 1
