@@ -502,6 +502,10 @@ def main() -> int:
             parity["stage1_records_ok"] = deep_ok
             parity["ok"] = parity["ok"] and deep_ok
         except Exception as e:    # noqa: BLE001 -- report, do not lose the line
+            try:                  # (a scan left pending would block the context for the sub-records)
+                ctx.resolve_batch_dev(frames.data_ptr(), cap)
+            except Exception:     # noqa: BLE001
+                pass
             parity["stage1_records_ok"] = False
             parity["stage1_records_error"] = str(e)[:120]
             parity["ok"] = False
