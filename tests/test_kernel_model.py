@@ -304,3 +304,31 @@ def test_dense_phase_lane_mapping_and_reciprocal():
         inv = (65536 + W - 1) // W
         for i in range(12 * W):
             assert (i * inv) >> 16 == i // W
+
+
+def test_host_only_entry_points(oracle_mod, golden_frames):
+    """The pure-host parts of the ABI need no GPU: getbits (mode_s/mod.rs:14-30) against the oracle's on random
+    messages and every (first, last) pair, icao_hash (icao_filter.rs:19-43), and the AVR line format the
+    reference writes to its TCP clients (main.rs:174-176)."""
+    import ctypes as C
+    L, O = _ffi.lib(), oracle_mod.lib()
+    rng = np.random.default_rng(8)
+    for _ in range(40):
+        m = bytes(rng.integers(0, 256, 14, dtype=np.uint8))
+        buf = (C.c_uint8 * 14).from_buffer_copy(m)
+        for a in range(1, 113, 7):
+            for b in range(a, min(a + 32, 113)):
+                assert L.b200adsb_getbits(m, a, b) == O.orc_getbits(buf, a, b), (m.hex(), a, b)
+    for a in [0, 1, 0xABCDEF, 0x4840D6, 0xFFFFFF, (1 << 25) | 0x123456] + [int(x) for x in rng.integers(0, 1 << 24, 200)]:
+        assert L.b200adsb_icao_hash(a) == O.orc_icao_hash(a)
+    frames = (_ffi.Frame * 2)()
+    msgs = [bytes.fromhex(golden_frames["test_1641427457780"][0]["hex"]), bytes.fromhex("02e1971ce17c84")]
+    for k, m in enumerate(msgs):
+        for i, byte in enumerate(m):
+            frames[k].msg[i] = byte
+        frames[k].len = len(m)
+    out = C.create_string_buffer(128)
+    n = C.c_size_t(0)
+    assert L.b200adsb_format_avr(frames, 2, out, 128, C.byref(n)) == 0
+    assert out.raw[: n.value].decode() == "".join("*" + m.hex() + ";\n" for m in msgs)
+    assert L.b200adsb_format_avr(frames, 2, out, 10, C.byref(n)) == _ffi.ERR_CAPACITY and n.value == 2 * 3 + 2 * (14 + 7)
