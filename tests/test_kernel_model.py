@@ -332,3 +332,35 @@ def test_host_only_entry_points(oracle_mod, golden_frames):
     assert L.b200adsb_format_avr(frames, 2, out, 128, C.byref(n)) == 0
     assert out.raw[: n.value].decode() == "".join("*" + m.hex() + ";\n" for m in msgs)
     assert L.b200adsb_format_avr(frames, 2, out, 10, C.byref(n)) == _ffi.ERR_CAPACITY and n.value == 2 * 3 + 2 * (14 + 7)
+
+
+def test_stage1_kernel_codegen():
+    """The built library carries the three compiled forms of the stage-1 kernel, and the standard-batch form
+    is the code the profiles describe: packed f32x2 arithmetic, the cp.async ring, shuffle-table CRC, no
+    local-memory traffic in the dense loop, and a footprint that stays inside the instruction
+    cache budget the kernel was tuned for (profiles/README.md: sensitive to code size)."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        import pytest
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", _ffi.SO_PATH], capture_output=True, text=True, timeout=300).stdout
+    funcs = {}
+    name = None
+    for line in out.splitlines():
+        if "Function :" in line:
+            name = line.split("Function :")[1].strip()
+            funcs[name] = []
+        elif name and line.strip().startswith("/*") and ";" in line:
+            funcs[name].append(line)
+    forms = {k: v for k, v in funcs.items() if "scan7_kernel" in k}
+    assert len(forms) == 4, sorted(forms)          # <true,0,false> <false,0,false> <false,7384,false> <false,7384,true>
+    std = next(v for k, v in forms.items() if "ILb0ELi7384ELb1" in k)
+    text = "\n".join(std)
+    assert 2800 < len(std) < 3200, len(std)
+    for mnemonic in ("FFMA2", "FADD2", "FMUL2", "LDGSTS", "SHFL.IDX", "MUFU.RSQ", "I2F.S16", "ATOMS", "BAR.SYNC"):
+        assert mnemonic in text, mnemonic
+    loop = next(i for i, ln in enumerate(std) if "DEPBAR.LE" in ln)          # the dense loop starts at the ring wait
+    assert not any("STL" in ln or "LDL" in ln for ln in std[loop:loop + 125]), "spills in the dense loop"
+    assert "HMMA" not in text and "UTCHMMA" not in text              # no tensor-core detour on this path
